@@ -1,0 +1,158 @@
+"""Oracle, inference-driver math (TEST INFRASTRUCTURE ONLY).
+
+Restates the NumPy/pandas arithmetic of:
+  * make_submission.py:120-153        TTA views, mean, argmax, label maps
+  * convert_from_see_v3_bugfix.py:61-110 / freeze_graph_32_classes.py:55-69
+                                      32 -> 12 class conversion, re-softmax, uint8
+  * create_pseudo_with_thresh.py:14-19,40-43   threshold selection
+  * majority_vote.py:26-56            N-way vote with fallback
+  * REPR_106_pseudo.py:12             3-way unanimity
+  * classes.py:5-41, input_data.py:49-60  class lists and orders
+"""
+from __future__ import annotations
+
+import numpy as np
+
+SILENCE_LABEL = "_silence_"
+UNKNOWN_WORD_LABEL = "_unknown_"
+WANTED_WORDS = "stop down off right up go on yes left no".split(" ")          # classes.py:7
+ALL_WORDS = ("sheila nine stop bed four six down bird marvin cat off right seven eight up "
+             "three happy go zero on wow dog yes five one tree house two left no").split(" ")  # classes.py:11
+# create_pseudo_with_thresh.py:9-10 / convert_from_see_v3_bugfix.py:67 ("Heng order")
+AUDIO_NAMES = ['silence', 'unknown', 'yes', 'no', 'up', 'down',
+               'left', 'right', 'on', 'off', 'stop', 'go']
+NUM_TEST_SAMPLES = 158538
+
+
+def int2label(wanted_only: bool):
+    """classes.py:31-36 via input_data.prepare_words_list."""
+    return [SILENCE_LABEL, UNKNOWN_WORD_LABEL] + (WANTED_WORDS if wanted_only else ALL_WORDS)
+
+
+def map_to_valid(labels):
+    """make_submission.py:16-24."""
+    return [{SILENCE_LABEL: "silence", UNKNOWN_WORD_LABEL: "unknown"}.get(l, l) for l in labels]
+
+
+def map_to_wanted(labels, wanted_words=None):
+    """make_submission.py:27-32 (wanted_words = prepare_words_list(get_classes(True)))."""
+    ww = set(int2label(True) if wanted_words is None else wanted_words)
+    return [l if (l in ww or l == "silence") else "unknown" for l in labels]
+
+
+# Shipped views (make_submission.py:126-128): identity, loud, left -- in the order
+# they are summed at :142-144.  (shift, gain): x_view[t] = gain * x[(t - shift) mod L].
+TTA_SHIPPED = [(0, 1.0), (0, 1.2), (-1500, 1.0)]
+# Synthetic "8x" table of SURVEY 8d, built from the primitives at
+# make_submission.py:126-130 and majority_vote.py:16-20.
+TTA_8 = [(0, 1.0), (-1500, 1.0), (0, 1.2), (0, 0.9), (0, -1.0), (-1500, 1.2), (-1500, 0.9),
+         (-3000, 1.0)]
+
+
+def tta_view(x: np.ndarray, shift: int, gain: float) -> np.ndarray:
+    """np.roll(X, shift, axis=1) then gain * X in fp32 (make_submission.py:126-130)."""
+    v = np.roll(np.asarray(x, np.float32), shift, axis=1)
+    if gain != 1.0:
+        v = (np.float32(gain) * v).astype(np.float32)
+    return v
+
+
+def tta_predict(predict, x: np.ndarray, views=TTA_SHIPPED):
+    """make_submission.py:120-146: sum the view probabilities in order, divide by
+    the view count, first-index argmax."""
+    acc = None
+    for shift, gain in views:
+        p = np.asarray(predict(tta_view(x, shift, gain)), np.float32)
+        acc = p if acc is None else (acc + p).astype(np.float32)
+    probs = (acc / np.float32(len(views))).astype(np.float32)
+    return probs, probs.argmax(axis=-1)
+
+
+def class_map_32_to_12(order: str = "heng"):
+    """For each of the 32 classes, the destination column in the 12-class vector.
+    order='heng'  : convert_from_see_v3_bugfix.py:67,76-92 (AUDIO_NAMES order)
+    order='frozen': freeze_graph_32_classes.py:55-69 (silence, unknown, then wanted
+                    words in ALL_WORDS order == the 12-class order of exp 195)."""
+    names32 = int2label(False)
+    if order == "heng":
+        target = AUDIO_NAMES
+    elif order == "frozen":
+        target = ["silence", "unknown"] + [w for w in ALL_WORDS if w in WANTED_WORDS]
+    else:
+        raise ValueError(order)
+    cmap = np.empty(32, np.int32)
+    for i, nm in enumerate(names32):
+        if nm == SILENCE_LABEL:
+            cmap[i] = 0
+        elif nm in target:
+            cmap[i] = target.index(nm)
+        else:                      # '_unknown_' and the 20 non-wanted words
+            cmap[i] = 1
+    return cmap
+
+
+def convert_32_to_12(all_probs: np.ndarray, order: str = "heng"):
+    """convert_from_see_v3_bugfix.py:76-110: unknown = max over the unknown group,
+    others copied; re-softmax WITHOUT max subtraction (:61-63) in fp32;
+    uint8 = trunc(p*255) (assignment into a uint8 memmap, :107-110)."""
+    all_probs = np.asarray(all_probs, np.float32)
+    cmap = class_map_32_to_12(order)
+    see = np.full((all_probs.shape[0], 12), -np.inf, np.float32)
+    for i in range(32):
+        see[:, cmap[i]] = np.maximum(see[:, cmap[i]], all_probs[:, i])
+    e = np.exp(see, dtype=np.float32)
+    sm = (e / e.sum(axis=1, keepdims=True, dtype=np.float32)).astype(np.float32)
+    u8 = (sm * np.float32(255)).astype(np.float32).astype(np.uint8)
+    return sm, u8
+
+
+def threshold_select(probs_u8: np.ndarray, prob_thresh: float):
+    """create_pseudo_with_thresh.py:17-18,40-43: max_probs = float32(max)/255;
+    preds = argmax (first index); a clip is DROPPED iff max_probs < prob_thresh.
+    Returns (preds int64, keep bool)."""
+    probs_u8 = np.asarray(probs_u8, np.uint8)
+    max_probs = np.float32(probs_u8.max(axis=-1)) / 255
+    preds = probs_u8.argmax(axis=-1)
+    keep = ~(max_probs.astype(np.float64) < float(prob_thresh))
+    return preds, keep
+
+
+def pseudo_counts(probs_u8: np.ndarray, prob_thresh: float):
+    """Counters printed by create_pseudo_with_thresh.py:65-66 (+ silence bookkeeping
+    :47-60: one noise wav per 30 kept silence clips)."""
+    preds, keep = threshold_select(probs_u8, prob_thresh)
+    silence_kept = int(np.sum(keep & (preds == 0)))
+    others_kept = int(np.sum(keep & (preds != 0)))
+    return dict(num_small_prob=int(np.sum(~keep)), kept=int(np.sum(keep)),
+                silence_kept=silence_kept, silence_files=silence_kept // 30,
+                num_labels=others_kept + silence_kept // 30)
+
+
+def majority_vote(labels: np.ndarray, min_count: int = 3):
+    """majority_vote.py:26-56 on integer labels [M,B]: the label with the highest
+    count (ties -> the one whose first occurrence comes from the earliest
+    submission, dict insertion order + max()); if that count < min_count fall
+    back to submission 0's label.  Returns (voted [B], clear_majority bool [B])."""
+    labels = np.asarray(labels)
+    M, B = labels.shape
+    out = np.empty(B, labels.dtype)
+    clear = np.zeros(B, bool)
+    for i in range(B):
+        counts = {}
+        for m in range(M):
+            ll = labels[m, i]
+            counts[ll] = counts.get(ll, 0) + 1
+        maj_label = max(counts, key=counts.get)
+        maj_count = max(counts.values())
+        if maj_count >= min_count:
+            clear[i] = True
+        else:
+            maj_label = labels[0, i]
+        out[i] = maj_label
+    return out, clear
+
+
+def unanimity(a, b, c):
+    """REPR_106_pseudo.py:12."""
+    a, b, c = np.asarray(a), np.asarray(b), np.asarray(c)
+    return (a == b) & (a == c)

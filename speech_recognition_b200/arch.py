@@ -1,0 +1,64 @@
+"""Architecture tables of the shipped raw-waveform networks.
+
+exp 195 / 206 = ``conv_1d_time_sliced_with_attention_model(filter_mult=1,
+num_classes=12)`` (reference model.py:775-838); exp 106 = the older 32-class
+variant recovered from the reference's ``logs_106`` GraphDef.
+Variable names are the Keras names found in those graphs, which is also how a
+Keras 2.1.2 HDF5 checkpoint / frozen .pb names them.
+"""
+from __future__ import annotations
+
+INPUT_SAMPLES = 16000
+PATCH, PATCH_STRIDE = 40, 20          # model.py:805  overlapping_time_slice_stack(x, 40, 20)
+BN_EPS = 1e-3                         # Keras BatchNormalization default
+
+ARCHS = {
+    195: dict(conv1=128, blocks=[(128, 1), (192, 2), (192, 1), (256, 2), (256, 1), (320, 2),
+                                 (320, 1), (384, 2), (384, 1), (512, 2), (512, 1)],
+              dense1_bias=True, pool="max_avg", classes=12),
+    106: dict(conv1=64, blocks=[(128, 1), (192, 2), (192, 1), (256, 2), (256, 1), (320, 2),
+                                (320, 1), (384, 2), (384, 1), (448, 2), (448, 1)],
+              dense1_bias=False, pool="attn_mean", classes=32),
+}
+ARCHS[206] = ARCHS[195]
+
+
+def same_pad(T: int, k: int, s: int):
+    """TF 'SAME': out = ceil(T/s), pad_left = pad_total // 2."""
+    out = -(-T // s)
+    total = max((out - 1) * s + k - T, 0)
+    return out, total // 2, total - total // 2
+
+
+def layer_lengths(arch: int, input_size: int = INPUT_SAMPLES):
+    """[n_patches, T after conv1d_1, T after each of the 11 blocks]."""
+    n_patch, _, _ = same_pad(input_size, PATCH, PATCH_STRIDE)
+    T = (n_patch - 3) // 2 + 1
+    out = [n_patch, T]
+    for _, s in ARCHS[arch]["blocks"]:
+        T = T - 2 if s == 1 else same_pad(T, 3, 2)[0]
+        out.append(T)
+    return out
+
+
+def weight_shapes(arch: int):
+    a = ARCHS[arch]
+    shapes = {}
+    c = a["conv1"]
+    shapes["conv1d_1/kernel"] = (3, PATCH, c)
+
+    def bn(i, ch):
+        for nm in ("gamma", "beta", "moving_mean", "moving_variance"):
+            shapes[f"batch_normalization_{i}/{nm}"] = (ch,)
+    bn(1, c)
+    for i, (co, _) in enumerate(a["blocks"], start=1):
+        shapes[f"depthwise_conv2d_{i}/depthwise_kernel"] = (1, 3, c, 1)
+        shapes[f"conv1d_{i + 1}/kernel"] = (1, c, co)
+        bn(i + 1, co)
+        c = co
+    T_last = layer_lengths(arch)[-1]
+    shapes["dense_1/kernel"] = (T_last * c, T_last)
+    if a["dense1_bias"]:
+        shapes["dense_1/bias"] = (T_last,)
+    shapes["dense_2/kernel"] = ((2 * c if a["pool"] == "max_avg" else c), a["classes"])
+    return shapes

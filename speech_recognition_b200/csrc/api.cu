@@ -1,0 +1,357 @@
+// C ABI of libkws.so (include/kws.h): argument validation, handle lifetime, the
+// host-buffer entry points (pinned-agnostic H2D/D2H pipeline on two streams) and
+// dispatch to the kernel launchers.  No CPU fallback exists anywhere below.
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+
+namespace kws {
+
+static thread_local std::string g_create_error;
+
+int fail(kws_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return code;
+}
+
+int ensure_bytes(kws_handle* h, void** p, size_t* cur, size_t need, bool pinned) {
+  if (*cur >= need && *p) return KWS_OK;
+  if (*p) { if (pinned) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *cur = 0; }
+  cudaError_t e = pinned ? cudaMallocHost(p, need) : cudaMalloc(p, need);
+  if (e != cudaSuccess) {
+    *p = nullptr;
+    return fail(h, KWS_ENOMEM, std::string("allocation of ") + std::to_string(need) + " bytes failed: " +
+                                   cudaGetErrorString(e));
+  }
+  *cur = need;
+  return KWS_OK;
+}
+
+static int make_views(kws_handle* h, const int32_t* shift_h, const float* gain_h, int n, ViewTable* vt) {
+  if (n <= 0 || n > KWS_MAX_VIEWS) return fail(h, KWS_EINVAL, "n_views must be in 1..16");
+  vt->n = n;
+  for (int i = 0; i < KWS_MAX_VIEWS; ++i) { vt->shift[i] = 0; vt->gain[i] = 1.0f; }
+  for (int i = 0; i < n; ++i) {
+    vt->shift[i] = shift_h ? shift_h[i] : 0;
+    vt->gain[i] = gain_h ? gain_h[i] : 1.0f;
+  }
+  return KWS_OK;
+}
+
+static int forward_dispatch(kws_handle* h, int slot, const float* wav, int B, const ViewTable& vt,
+                            float* probs, int32_t* argmax, cudaStream_t st) {
+  if (slot < 0 || slot >= KWS_MAX_MODELS || !h->models[slot].loaded)
+    return fail(h, KWS_ESTATE, "kws_forward before kws_model_load for this slot");
+  if (B < 0) return fail(h, KWS_EINVAL, "negative batch");
+  if (B == 0) return KWS_OK;
+  if (!wav) return fail(h, KWS_EINVAL, "null waveform pointer");
+  return h->precision == KWS_PREC_FP32 ? launch_forward_f32(h, h->models[slot], wav, B, vt, probs, argmax, st)
+                                       : launch_forward_tc(h, h->models[slot], wav, B, vt, probs, argmax, st);
+}
+
+static int features_dispatch(kws_handle* h, const float* wav, int B, int kind, float* out, cudaStream_t st) {
+  if (!h->fe.configured) return fail(h, KWS_ESTATE, "kws_features before kws_frontend_config");
+  if (kind < KWS_FEAT_SPEC || kind > KWS_FEAT_MFCC) return fail(h, KWS_EINVAL, "unknown feature kind");
+  if (B < 0) return fail(h, KWS_EINVAL, "negative batch");
+  if (B == 0) return KWS_OK;
+  if (!wav || !out) return fail(h, KWS_EINVAL, "null pointer");
+  return h->precision == KWS_PREC_FP32 ? launch_features_f32(h, wav, B, kind, out, st)
+                                       : launch_features_tc(h, wav, B, kind, out, st);
+}
+
+static size_t feat_dim(const kws_handle* h, int kind) {
+  const Frontend& fe = h->fe;
+  const int d = kind == KWS_FEAT_SPEC ? fe.n_bins : (kind == KWS_FEAT_LOGMEL ? fe.n_mel : fe.n_keep);
+  return static_cast<size_t>(fe.frames) * d;
+}
+
+}  // namespace kws
+
+using namespace kws;
+
+extern "C" {
+
+int kws_abi_version(void) { return KWS_ABI_VERSION; }
+
+const char* kws_last_error(const kws_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int64_t kws_launch_count(const kws_t* h) { return h ? h->launches : 0; }
+
+int kws_create(kws_t** out, int device, int max_rows) {
+  if (!out) return fail(nullptr, KWS_EINVAL, "null handle pointer");
+  *out = nullptr;
+  if (max_rows <= 0) return fail(nullptr, KWS_EINVAL, "max_rows must be positive");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, KWS_ECUDA, std::string("no CUDA device: libkws has no CPU fallback (") +
+                                        cudaGetErrorString(e) + ")");
+  if (device < 0 || device >= n) return fail(nullptr, KWS_EINVAL, "device index out of range");
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, KWS_ECUDA, cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(nullptr, KWS_ECUDA, cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, KWS_EUNSUPPORTED, std::string("libkws is built for sm_100a (B200); found ") + prop.name);
+  kws_handle* h = new (std::nothrow) kws_handle();
+  if (!h) return fail(nullptr, KWS_ENOMEM, "out of host memory");
+  h->device = device; h->max_rows = max_rows; h->num_sms = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    delete h; return fail(nullptr, KWS_ECUDA, cudaGetErrorString(e));
+  }
+  *out = h;
+  return KWS_OK;
+}
+
+void kws_destroy(kws_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < KWS_MAX_MODELS; ++i) {
+    if (h->models[i].blob) cudaFree(h->models[i].blob);
+    if (h->models[i].tc_blob) cudaFree(h->models[i].tc_blob);
+  }
+  if (h->fe.blob) cudaFree(h->fe.blob);
+  if (h->fe.tc_blob) cudaFree(h->fe.tc_blob);
+  if (h->file_offsets_d) cudaFree(h->file_offsets_d);
+  for (int i = 0; i < 2; ++i) if (h->act[i]) cudaFree(h->act[i]);
+  if (h->spec_ws) cudaFree(h->spec_ws);
+  if (h->mel_ws) cudaFree(h->mel_ws);
+  if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->stage_d) cudaFree(h->stage_d);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+int kws_set_precision(kws_t* h, int precision) {
+  if (!h) return KWS_EINVAL;
+  if (precision != KWS_PREC_FP32 && precision != KWS_PREC_TC) return fail(h, KWS_EINVAL, "unknown precision");
+  h->precision = precision;
+  return KWS_OK;
+}
+
+int kws_set_noise_bank(kws_t* h, const float* bank, const int64_t* file_offsets_h, int n_files) {
+  if (!h) return KWS_EINVAL;
+  if (n_files < 0 || (n_files > 0 && (!bank || !file_offsets_h))) return fail(h, KWS_EINVAL, "bad noise bank");
+  if (reinterpret_cast<uintptr_t>(bank) % 16) return fail(h, KWS_EINVAL, "noise bank must be 16-byte aligned");
+  KWS_CUDA(h, cudaSetDevice(h->device));
+  if (h->file_offsets_d) { cudaFree(h->file_offsets_d); h->file_offsets_d = nullptr; }
+  h->bank = bank; h->n_files = n_files; h->bank_len = 0;
+  if (n_files == 0) return KWS_OK;
+  for (int i = 0; i < n_files; ++i)
+    if (file_offsets_h[i + 1] - file_offsets_h[i] <= KWS_SAMPLES)
+      return fail(h, KWS_EINVAL, "every background file must be longer than one clip (input_data.py:485-486)");
+  h->bank_len = file_offsets_h[n_files];
+  KWS_CUDA(h, cudaMalloc(&h->file_offsets_d, (n_files + 1) * sizeof(int64_t)));
+  KWS_CUDA(h, cudaMemcpy(h->file_offsets_d, file_offsets_h, (n_files + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+  return KWS_OK;
+}
+
+static int augment_common(kws_t* h, const float* wav, const int16_t* pcm, float divisor, const int32_t* shift,
+                          const int32_t* bg_file, const int32_t* bg_off, const float* bg_vol,
+                          const float* fg_vol, float* out, int B, int clamp, void* stream) {
+  if (!h) return KWS_EINVAL;
+  if (B < 0) return fail(h, KWS_EINVAL, "negative batch");
+  if (B == 0) return KWS_OK;
+  if ((!wav && !pcm) || !shift || !bg_file || !bg_off || !bg_vol || !fg_vol || !out)
+    return fail(h, KWS_EINVAL, "null pointer");
+  const void* in = wav ? static_cast<const void*>(wav) : static_cast<const void*>(pcm);
+  if (reinterpret_cast<uintptr_t>(in) % 16 || reinterpret_cast<uintptr_t>(out) % 16)
+    return fail(h, KWS_EINVAL, "waveform buffers must be 16-byte aligned");
+  return launch_augment(h, wav, pcm, divisor, shift, bg_file, bg_off, bg_vol, fg_vol, out, B, clamp,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int kws_augment(kws_t* h, const float* wav, const int32_t* shift, const int32_t* bg_file,
+                const int32_t* bg_off, const float* bg_vol, const float* fg_vol, float* out, int B,
+                int clamp, void* stream) {
+  return augment_common(h, wav, nullptr, 1.0f, shift, bg_file, bg_off, bg_vol, fg_vol, out, B, clamp, stream);
+}
+
+int kws_augment_pcm16(kws_t* h, const int16_t* pcm, float divisor, const int32_t* shift,
+                      const int32_t* bg_file, const int32_t* bg_off, const float* bg_vol,
+                      const float* fg_vol, float* out, int B, int clamp, void* stream) {
+  if (h && !(divisor > 0.0f)) return fail(h, KWS_EINVAL, "divisor must be positive");
+  return augment_common(h, nullptr, pcm, divisor, shift, bg_file, bg_off, bg_vol, fg_vol, out, B, clamp, stream);
+}
+
+int kws_frontend_config(kws_t* h, int win, int hop, int n_mel, int n_keep, float f_lo, float f_hi, int sample_rate) {
+  if (!h) return KWS_EINVAL;
+  KWS_CUDA(h, cudaSetDevice(h->device));
+  return frontend_build(h, win, hop, n_mel, n_keep, f_lo, f_hi, sample_rate);
+}
+
+int kws_frontend_frames(const kws_t* h) { return (h && h->fe.configured) ? h->fe.frames : 0; }
+
+int kws_features(kws_t* h, const float* wav, int B, int kind, float* out, void* stream) {
+  if (!h) return KWS_EINVAL;
+  return features_dispatch(h, wav, B, kind, out, static_cast<cudaStream_t>(stream));
+}
+
+int kws_model_load(kws_t* h, int slot, int arch, const kws_tensor_h* tensors_h, int n) {
+  if (!h) return KWS_EINVAL;
+  if (!tensors_h || n <= 0) return fail(h, KWS_EINVAL, "no tensors");
+  KWS_CUDA(h, cudaSetDevice(h->device));
+  return model_build(h, slot, arch, tensors_h, n);
+}
+
+int kws_model_classes(const kws_t* h, int slot) {
+  if (!h || slot < 0 || slot >= KWS_MAX_MODELS || !h->models[slot].loaded) return 0;
+  return h->models[slot].classes;
+}
+
+int kws_forward(kws_t* h, int slot, const float* wav, int B, const int32_t* view_shift_h,
+                const float* view_gain_h, int n_views, float* probs_mean, int32_t* argmax, void* stream) {
+  if (!h) return KWS_EINVAL;
+  ViewTable vt;
+  int rc = make_views(h, view_shift_h, view_gain_h, n_views, &vt);
+  if (rc) return rc;
+  return forward_dispatch(h, slot, wav, B, vt, probs_mean, argmax, static_cast<cudaStream_t>(stream));
+}
+
+int kws_convert_classes(kws_t* h, const float* probs, int B, int C_in, const int32_t* class_map_h,
+                        int C_out, float* probs_out, uint8_t* probs_u8, void* stream) {
+  if (!h) return KWS_EINVAL;
+  if (B < 0 || !class_map_h || (B > 0 && !probs)) return fail(h, KWS_EINVAL, "bad arguments");
+  return launch_convert(h, probs, B, C_in, class_map_h, C_out, probs_out, probs_u8, static_cast<cudaStream_t>(stream));
+}
+
+int kws_select(kws_t* h, const uint8_t* probs_u8, int B, int C, double thresh, int32_t* label,
+               uint8_t* keep, void* stream) {
+  if (!h) return KWS_EINVAL;
+  if (B < 0 || (B > 0 && !probs_u8)) return fail(h, KWS_EINVAL, "bad arguments");
+  return launch_select(h, probs_u8, B, C, thresh, label, keep, static_cast<cudaStream_t>(stream));
+}
+
+int kws_vote(kws_t* h, const int32_t* labels, int M, int B, int min_count, int32_t* voted,
+             uint8_t* clear, void* stream) {
+  if (!h) return KWS_EINVAL;
+  if (B < 0 || (B > 0 && !labels)) return fail(h, KWS_EINVAL, "bad arguments");
+  return launch_vote(h, labels, M, B, min_count, voted, clear, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------
+// Host-buffer entry points.  One staging allocation on the device holds, per call, the
+// waveforms, parameters and results; copies and kernels are enqueued on the handle's own
+// stream in chunks so the H2D copy of chunk k+1 queues behind the kernels of chunk k.
+// Pinned caller buffers make the copies truly asynchronous; pageable ones still work.
+// ------------------------------------------------------------------------------------------
+struct StageLayout {
+  size_t wav, aug, shift, bgf, bgo, bgv, fgv, feat, probs, amax, total;
+};
+
+static StageLayout stage_layout(const kws_handle* h, int nb, int classes, size_t fdim) {
+  StageLayout s{};
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
+  s.wav = take(static_cast<size_t>(nb) * L * 4);
+  s.aug = take(static_cast<size_t>(nb) * L * 4);
+  s.shift = take(nb * 4); s.bgf = take(nb * 4); s.bgo = take(nb * 4); s.bgv = take(nb * 4); s.fgv = take(nb * 4);
+  s.feat = take(static_cast<size_t>(nb) * fdim * 4);
+  s.probs = take(static_cast<size_t>(nb) * classes * 4);
+  s.amax = take(nb * 4);
+  s.total = o;
+  (void)h;
+  return s;
+}
+
+int kws_pipeline_host(kws_t* h, int slot, const float* wav_h, const int32_t* shift_h,
+                      const int32_t* bg_file_h, const int32_t* bg_off_h, const float* bg_vol_h,
+                      const float* fg_vol_h, int B, int feat_kind, const int32_t* view_shift_h,
+                      const float* view_gain_h, int n_views, float* feat_h, float* probs_h,
+                      int32_t* argmax_h) {
+  if (!h) return KWS_EINVAL;
+  if (B < 0) return fail(h, KWS_EINVAL, "negative batch");
+  if (B == 0) return KWS_OK;
+  if (!wav_h) return fail(h, KWS_EINVAL, "null waveform pointer");
+  KWS_CUDA(h, cudaSetDevice(h->device));
+  const bool do_aug = shift_h || bg_file_h || bg_off_h || bg_vol_h || fg_vol_h;
+  if (do_aug && !(shift_h && bg_file_h && bg_off_h && bg_vol_h && fg_vol_h))
+    return fail(h, KWS_EINVAL, "augmentation parameters must be all present or all NULL");
+  const bool do_feat = feat_kind >= 0;
+  const bool do_fwd = n_views > 0;
+  if (do_feat && !h->fe.configured) return fail(h, KWS_ESTATE, "front end not configured");
+  ViewTable vt{};
+  int classes = 0;
+  if (do_fwd) {
+    int rc = make_views(h, view_shift_h, view_gain_h, n_views, &vt);
+    if (rc) return rc;
+    if (slot < 0 || slot >= KWS_MAX_MODELS || !h->models[slot].loaded) return fail(h, KWS_ESTATE, "model not loaded");
+    classes = h->models[slot].classes;
+  }
+  const size_t fdim = do_feat ? feat_dim(h, feat_kind) : 0;
+  const int chunk = std::max(1, std::min(B, do_fwd ? std::max(1, h->max_rows / n_views) * 4 : 8192));
+  const StageLayout lay = stage_layout(h, chunk, std::max(classes, 1), fdim);
+  // two staging slots so the copy of the next chunk can be queued while this one computes
+  int rc = ensure_bytes(h, &h->stage_d, &h->stage_bytes, 2 * lay.total);
+  if (rc) return rc;
+  cudaStream_t st = h->own_stream;
+  int k = 0;
+  for (int b0 = 0; b0 < B; b0 += chunk, ++k) {
+    const int nb = std::min(chunk, B - b0);
+    char* base = static_cast<char*>(h->stage_d) + (k & 1) * lay.total;
+    float* d_wav = reinterpret_cast<float*>(base + lay.wav);
+    float* d_aug = reinterpret_cast<float*>(base + lay.aug);
+    KWS_CUDA(h, cudaMemcpyAsync(d_wav, wav_h + static_cast<size_t>(b0) * L, static_cast<size_t>(nb) * L * 4,
+                                cudaMemcpyHostToDevice, st));
+    const float* x = d_wav;
+    if (do_aug) {
+      int32_t* d_shift = reinterpret_cast<int32_t*>(base + lay.shift);
+      int32_t* d_bgf = reinterpret_cast<int32_t*>(base + lay.bgf);
+      int32_t* d_bgo = reinterpret_cast<int32_t*>(base + lay.bgo);
+      float* d_bgv = reinterpret_cast<float*>(base + lay.bgv);
+      float* d_fgv = reinterpret_cast<float*>(base + lay.fgv);
+      KWS_CUDA(h, cudaMemcpyAsync(d_shift, shift_h + b0, nb * 4, cudaMemcpyHostToDevice, st));
+      KWS_CUDA(h, cudaMemcpyAsync(d_bgf, bg_file_h + b0, nb * 4, cudaMemcpyHostToDevice, st));
+      KWS_CUDA(h, cudaMemcpyAsync(d_bgo, bg_off_h + b0, nb * 4, cudaMemcpyHostToDevice, st));
+      KWS_CUDA(h, cudaMemcpyAsync(d_bgv, bg_vol_h + b0, nb * 4, cudaMemcpyHostToDevice, st));
+      KWS_CUDA(h, cudaMemcpyAsync(d_fgv, fg_vol_h + b0, nb * 4, cudaMemcpyHostToDevice, st));
+      rc = launch_augment(h, d_wav, nullptr, 1.0f, d_shift, d_bgf, d_bgo, d_bgv, d_fgv, d_aug, nb, 0, st);
+      if (rc) return rc;
+      x = d_aug;
+    }
+    if (do_feat) {
+      float* d_feat = reinterpret_cast<float*>(base + lay.feat);
+      rc = features_dispatch(h, x, nb, feat_kind, d_feat, st);
+      if (rc) return rc;
+      if (feat_h)
+        KWS_CUDA(h, cudaMemcpyAsync(feat_h + static_cast<size_t>(b0) * fdim, d_feat, static_cast<size_t>(nb) * fdim * 4,
+                                    cudaMemcpyDeviceToHost, st));
+    } else if (feat_h && !do_fwd) {                      // 'raw' representation: the augmented waveform
+      KWS_CUDA(h, cudaMemcpyAsync(feat_h + static_cast<size_t>(b0) * L, x, static_cast<size_t>(nb) * L * 4,
+                                  cudaMemcpyDeviceToHost, st));
+    }
+    if (do_fwd) {
+      float* d_probs = reinterpret_cast<float*>(base + lay.probs);
+      int32_t* d_amax = reinterpret_cast<int32_t*>(base + lay.amax);
+      rc = forward_dispatch(h, slot, x, nb, vt, d_probs, d_amax, st);
+      if (rc) return rc;
+      if (probs_h)
+        KWS_CUDA(h, cudaMemcpyAsync(probs_h + static_cast<size_t>(b0) * classes, d_probs,
+                                    static_cast<size_t>(nb) * classes * 4, cudaMemcpyDeviceToHost, st));
+      if (argmax_h)
+        KWS_CUDA(h, cudaMemcpyAsync(argmax_h + b0, d_amax, nb * 4, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  KWS_CUDA(h, cudaStreamSynchronize(st));
+  return KWS_OK;
+}
+
+int kws_predict_host(kws_t* h, int slot, const float* wav_h, int B, const int32_t* view_shift_h,
+                     const float* view_gain_h, int n_views, float* probs_h, int32_t* argmax_h) {
+  if (h && n_views <= 0) return fail(h, KWS_EINVAL, "n_views must be positive");
+  return kws_pipeline_host(h, slot, wav_h, nullptr, nullptr, nullptr, nullptr, nullptr, B, -1, view_shift_h,
+                           view_gain_h, n_views, nullptr, probs_h, argmax_h);
+}
+
+int kws_get_data_host(kws_t* h, const float* wav_h, const int32_t* shift_h, const int32_t* bg_file_h,
+                      const int32_t* bg_off_h, const float* bg_vol_h, const float* fg_vol_h, int B,
+                      int clamp, int kind, float* out_h) {
+  if (h && clamp) return fail(h, KWS_EUNSUPPORTED, "clamp is only available through kws_augment");
+  if (h && !out_h) return fail(h, KWS_EINVAL, "null output pointer");
+  return kws_pipeline_host(h, 0, wav_h, shift_h, bg_file_h, bg_off_h, bg_vol_h, fg_vol_h, B, kind, nullptr,
+                           nullptr, 0, out_h, nullptr, nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,139 @@
+// Internal declarations shared by the libkws.so translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/kws.h"
+
+namespace kws {
+
+constexpr int L = KWS_SAMPLES;           // samples per clip
+constexpr int NUM_BLOCKS = 11;           // depthwise-separable blocks after conv1d_1
+constexpr int NUM_SMS_B200 = 148;
+
+struct ViewTable {                        // TTA views, passed to kernels by value
+  int   n;
+  int   shift[KWS_MAX_VIEWS];             // np.roll shift
+  float gain[KWS_MAX_VIEWS];
+};
+
+struct LayerDesc {                        // one depthwise-separable block (model.py:34-52)
+  int cin, cout, stride, pad_left, t_in, t_out;
+};
+
+struct Model {
+  bool loaded = false;
+  int arch = 0, classes = 0, c0 = 0, t0 = 0, t_last = 0, c_last = 0;
+  bool dense1_bias = false, pool_max_avg = false;
+  LayerDesc layers[NUM_BLOCKS];
+  // fp32 device weights (Keras layouts), all inside one allocation `blob`
+  float* blob = nullptr;
+  float* w_conv1 = nullptr;               // [120, c0]
+  float* bn_scale[NUM_BLOCKS + 1];        // s = rsqrt(var+eps)*gamma
+  float* bn_shift[NUM_BLOCKS + 1];        // beta - mean*s
+  float* w_dw[NUM_BLOCKS];                // [3, cin]
+  float* w_pw[NUM_BLOCKS];                // [cin, cout]
+  float* w_d1 = nullptr;                  // [t_last*c_last, t_last]
+  float* b_d1 = nullptr;                  // [t_last] (zeros when the arch has no bias)
+  float* w_d2 = nullptr;                  // [feat, classes]
+  // tensor-core operand images (bf16, pre-swizzled UMMA K-major SW128 slabs)
+  void* tc_blob = nullptr;
+  __nv_bfloat16* tc_conv1 = nullptr;      // [kblocks][c0 rows][64] swizzled
+  __nv_bfloat16* tc_pw[NUM_BLOCKS];       // [kblocks][cout rows][64] swizzled
+  size_t max_act_elems = 0;               // max over layers of T*C (per clip-view)
+};
+
+struct Frontend {
+  bool configured = false;
+  int win = 0, hop = 0, n_fft = 0, n_bins = 0, frames = 0, n_mel = 0, n_keep = 0;
+  float* blob = nullptr;
+  float* dft_basis = nullptr;             // [win, 2*n_bins] interleaved (cos*w, -sin*w)
+  float* mel_w = nullptr;                 // [n_bins, n_mel]
+  float* dct_w = nullptr;                 // [n_mel, n_keep]
+  // sparse mel (each bin feeds <= 2 filters)
+  int*   mel_idx = nullptr;               // [n_bins][2]
+  float* mel_val = nullptr;               // [n_bins][2]
+  void*  tc_blob = nullptr;               // split-fp16 DFT basis images for the tcgen05 path
+  __half* tc_basis_hi = nullptr;
+  __half* tc_basis_lo = nullptr;
+  int tc_kblocks = 0, tc_ncols = 0;
+};
+
+}  // namespace kws
+
+struct kws_handle {
+  int device = 0;
+  int max_rows = 0;
+  int precision = KWS_PREC_TC;
+  int num_sms = kws::NUM_SMS_B200;
+  std::string err;
+  int64_t launches = 0;
+  // noise bank (caller-owned device memory)
+  const float* bank = nullptr;
+  int64_t bank_len = 0;
+  int n_files = 0;
+  int64_t* file_offsets_d = nullptr;      // device copy [n_files+1]
+  kws::Frontend fe;
+  kws::Model models[KWS_MAX_MODELS];
+  // workspace
+  void* act[2] = {nullptr, nullptr};      // ping-pong activations
+  size_t act_bytes = 0;
+  float* spec_ws = nullptr;               // frontend intermediates (fp32 path)
+  size_t spec_ws_bytes = 0;
+  float* mel_ws = nullptr;
+  size_t mel_ws_bytes = 0;
+  // host-entry staging
+  void* pinned = nullptr;  size_t pinned_bytes = 0;
+  void* stage_d = nullptr; size_t stage_bytes = 0;
+  cudaStream_t own_stream = nullptr;
+};
+
+namespace kws {
+
+int fail(kws_handle* h, int code, const std::string& msg);
+int ensure_bytes(kws_handle* h, void** p, size_t* cur, size_t need, bool pinned = false);
+
+#define KWS_CUDA(h, expr)                                                              \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess)                                                             \
+      return kws::fail((h), KWS_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+#define KWS_LAUNCH_CHECK(h)                                                            \
+  do {                                                                                 \
+    (h)->launches++;                                                                   \
+    cudaError_t _e = cudaGetLastError();                                               \
+    if (_e != cudaSuccess)                                                             \
+      return kws::fail((h), KWS_ECUDA, std::string("kernel launch at ") + __FILE__ + ":" + \
+                                           std::to_string(__LINE__) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+// ---- launchers implemented in the .cu files ----
+int launch_augment(kws_handle* h, const float* wav, const int16_t* pcm, float pcm_scale,
+                   const int32_t* shift, const int32_t* bg_file, const int32_t* bg_off,
+                   const float* bg_vol, const float* fg_vol, float* out, int B, int clamp,
+                   cudaStream_t st);
+int frontend_build(kws_handle* h, int win, int hop, int n_mel, int n_keep, float f_lo, float f_hi,
+                   int sample_rate);
+int launch_features_f32(kws_handle* h, const float* wav, int B, int kind, float* out, cudaStream_t st);
+int launch_features_tc(kws_handle* h, const float* wav, int B, int kind, float* out, cudaStream_t st);
+int model_build(kws_handle* h, int slot, int arch, const kws_tensor_h* t, int n);
+int launch_forward_f32(kws_handle* h, Model& m, const float* wav, int B, const ViewTable& vt,
+                       float* probs_mean, int32_t* argmax, cudaStream_t st);
+int launch_forward_tc(kws_handle* h, Model& m, const float* wav, int B, const ViewTable& vt,
+                      float* probs_mean, int32_t* argmax, cudaStream_t st);
+int launch_head(kws_handle* h, Model& m, const void* act, bool act_bf16, int n_clips, int n_views,
+                float* probs_mean, int32_t* argmax, cudaStream_t st);
+int launch_convert(kws_handle* h, const float* probs, int B, int C_in, const int32_t* class_map_h,
+                   int C_out, float* probs_out, uint8_t* probs_u8, cudaStream_t st);
+int launch_select(kws_handle* h, const uint8_t* probs_u8, int B, int C, double thresh,
+                  int32_t* label, uint8_t* keep, cudaStream_t st);
+int launch_vote(kws_handle* h, const int32_t* labels, int M, int B, int min_count, int32_t* voted,
+                uint8_t* clear, cudaStream_t st);
+
+}  // namespace kws

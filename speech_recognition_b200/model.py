@@ -1,0 +1,48 @@
+"""``load_model`` / ``Model.predict`` -- the Keras-shaped surface of the reference
+(make_submission.py:64-71,120-146) on top of libkws.so."""
+from __future__ import annotations
+
+import numpy as np
+
+from .engine import Engine
+from .weights import load_weights, validate, infer_arch
+
+# make_submission.py:126-128, in the order they are summed at :142-144
+TTA_SHIPPED = ((0, 1.0), (0, 1.2), (-1500, 1.0))
+# synthetic 8-view table of SURVEY.md 8d (built from make_submission.py:126-130 primitives)
+TTA_8 = ((0, 1.0), (-1500, 1.0), (0, 1.2), (0, 0.9), (0, -1.0), (-1500, 1.2), (-1500, 0.9), (-3000, 1.0))
+
+
+class Model:
+    """Stateless, synchronous ``predict`` like keras.Model (inference mode: BN moving
+    statistics, dropout off -- K.set_learning_phase(0), make_submission.py:37)."""
+
+    def __init__(self, arch: int, weights: dict, engine: Engine | None = None, slot: int = 0,
+                 device: int = 0, precision="tc"):
+        self.engine = engine if engine is not None else Engine(device=device, precision=precision)
+        self.slot = slot
+        self.arch = arch
+        self.weights = validate(arch, weights)
+        self.num_classes = self.engine.load_model(slot, arch, self.weights)
+
+    def predict(self, x, batch_size=32, verbose=0, views=((0, 1.0),)):
+        """x: float32 [N,16000] -> float32 [N,C] softmax probabilities.  ``batch_size`` is
+        accepted for API compatibility; the device batches internally."""
+        x = np.ascontiguousarray(x, np.float32)
+        if x.ndim != 2 or x.shape[1] != 16000:
+            raise ValueError("Error when checking input: expected input_1 to have shape (None, 16000) "
+                             "but got array with shape %s" % (x.shape,))
+        probs, _ = self.engine.predict_host(x, views=views, slot=self.slot)
+        return probs
+
+    def predict_tta(self, x, views=TTA_SHIPPED):
+        """(probs + loud_probs + left_probs) / 3 and argmax (make_submission.py:120-146)."""
+        x = np.ascontiguousarray(x, np.float32)
+        return self.engine.predict_host(x, views=views, slot=self.slot)
+
+
+def load_model(filepath, custom_objects=None, engine: Engine | None = None, slot: int = 0, **kw):
+    """keras.models.load_model stand-in: .npz / Keras .hdf5 / frozen .pb -> Model.
+    ``custom_objects`` is accepted and ignored (relu6, DepthwiseConv2D, ... are built in)."""
+    arch, weights = load_weights(filepath)
+    return Model(arch, weights, engine=engine, slot=slot, **kw)

@@ -1,0 +1,240 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU oracle
+on identical seeded inputs, weights and pre-drawn parameters.
+
+Tolerances (BASELINE.json north_star): shift / noise indices / argmax labels bit-exact;
+the fp32 tier within 1e-4 relative; the tensor-core tier (bf16 / split-fp16 operands) within 1e-2."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import augment, frontend, network, driver
+from speech_recognition_b200 import synth, TTA_SHIPPED, TTA_8
+from speech_recognition_b200.classes import class_map_32_to_12
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def rel_err(a, b):
+    """max |a-b| relative to the scale of the reference tensor."""
+    return float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max() / (np.abs(b).max() + 1e-30))
+
+
+# --------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("B", [1, 7, 64])
+def test_augment_bit_exact(engine, synth_small, B):
+    clips = synth.make_clips(B, seed=100 + B)
+    bank, offs = synth_small["bank"], synth_small["offsets"]
+    p = synth.make_params(B, offs, seed=200 + B)
+    # edge cases of the roll and the noise slice
+    p["time_shift"][0] = 0
+    if B > 3:
+        p["time_shift"][1], p["time_shift"][2], p["time_shift"][3] = -500, 16000 + 3, -16001
+        p["bg_index"][2] = -1                                   # "no background" -> zeros
+        p["bg_index"][3] = len(offs) - 2
+        p["bg_offset"][3] = int(offs[-1] - offs[-2]) - 16000 - 1   # last legal slice of the last file
+        p["bg_volume"][3] = 0.25
+    bank_t = dev(bank)
+    engine.set_noise_bank(bank_t, offs)
+    out = engine.augment(dev(clips), dev(p["time_shift"]), dev(p["bg_index"]), dev(p["bg_offset"]),
+                         dev(p["bg_volume"]), dev(p["fg_volume"]))
+    torch.cuda.synchronize()
+    bg = augment.gather_background(bank, offs, p["bg_index"], p["bg_offset"])
+    ref = augment.augment_mix(clips, p["time_shift"], bg, p["bg_volume"], p["fg_volume"])
+    got = out.cpu().numpy()
+    assert got.dtype == np.float32
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), "K1 must be bit-exact"
+
+
+def test_augment_clamp_and_pcm16(engine, synth_small):
+    B = 9
+    clips, pcm = synth.make_clips(B, seed=31, return_pcm=True)
+    bank, offs = synth_small["bank"], synth_small["offsets"]
+    p = synth.make_params(B, offs, seed=32)
+    p["fg_volume"][:] = 4.0                                     # force clipping
+    engine.set_noise_bank(dev(bank), offs)
+    args = [dev(p[k]) for k in ("time_shift", "bg_index", "bg_offset", "bg_volume", "fg_volume")]
+    bg = augment.gather_background(bank, offs, p["bg_index"], p["bg_offset"])
+    got = engine.augment(dev(clips), *args, clamp=True).cpu().numpy()
+    ref = augment.augment_mix(clips, p["time_shift"], bg, p["bg_volume"], p["fg_volume"], clamp=True)
+    assert np.array_equal(got, ref) and got.max() == 1.0
+    for divisor, scale in ((32768.0, "tf"), (32767.0, "scipy")):
+        got = engine.augment(dev(pcm), *args, pcm_divisor=divisor).cpu().numpy()
+        ref = augment.augment_mix(augment.decode_pcm16(pcm, scale=scale), p["time_shift"], bg,
+                                  p["bg_volume"], p["fg_volume"])
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), scale
+
+
+def test_augment_empty_batch(engine):
+    z = torch.empty((0, 16000), dtype=torch.float32, device=DEV)
+    zi = torch.empty((0,), dtype=torch.int32, device=DEV)
+    zf = torch.empty((0,), dtype=torch.float32, device=DEV)
+    assert engine.augment(z, zi, zi, zi, zf, zf).shape == (0, 16000)
+
+
+def test_augment_roll_property_full_size(engine):
+    """Size-independent property at a bench-size batch: with fg=1, no background, the output is a
+    permutation of the input (np.roll) and roll(roll(x, s), -s) == x bit for bit."""
+    B = 4096
+    g = torch.Generator(device=DEV).manual_seed(5)
+    x = (torch.randn((B, 16000), device=DEV, generator=g) * 0.1)
+    s = torch.randint(-20000, 20000, (B,), device=DEV, generator=g, dtype=torch.int32)
+    none = torch.full((B,), -1, dtype=torch.int32, device=DEV)
+    zi = torch.zeros((B,), dtype=torch.int32, device=DEV)
+    zf = torch.zeros((B,), dtype=torch.float32, device=DEV)
+    one = torch.ones((B,), dtype=torch.float32, device=DEV)
+    y = engine.augment(x, s, none, zi, zf, one)
+    back = engine.augment(y, -s, none, zi, zf, one)
+    assert torch.equal(back, x + 0.0)
+    i = 1234
+    assert torch.equal(y[i], torch.roll(x[i], int(s[i])))
+
+
+# --------------------------------------------------------------------------- K2-K4
+@pytest.mark.parametrize("n_mel,n_keep,win,hop", [(40, 40, 480, 160), (80, 60, 400, 240)])
+def test_features_fp32(engine, n_mel, n_keep, win, hop):
+    engine.set_precision("fp32")
+    engine.frontend_config(win, hop, n_mel, n_keep)
+    x = synth.make_clips(6, seed=77)
+    xt = dev(x)
+    spec = engine.features(xt, "spec").cpu().numpy()
+    lm = engine.features(xt, "logmel").cpu().numpy()
+    mf = engine.features(xt, "mfcc").cpu().numpy()
+    r_spec = frontend.features(x, window_size_samples=win, window_stride_samples=hop, kind="spec")
+    r_lm = frontend.features(x, window_size_samples=win, window_stride_samples=hop,
+                             dct_coefficient_count=n_mel, kind="logmel")
+    r_mf = frontend.features(x, window_size_samples=win, window_stride_samples=hop,
+                             dct_coefficient_count=n_mel, num_log_mel_features=n_keep, kind="mfcc")
+    assert spec.shape == r_spec.shape and lm.shape == r_lm.shape and mf.shape == r_mf.shape
+    # fp32 tier: 1e-4 relative to the tensor scale (a low-energy bin next to a loud one is not
+    # reproducible to 1e-4 of its OWN value between two fp32 FFT orders either)
+    assert rel_err(spec, r_spec) < 1e-5
+    assert rel_err(lm, r_lm) < 1e-4
+    assert rel_err(mf, r_mf) < 1e-4
+    # log-mel of bins that are not buried: elementwise 1e-4 relative
+    loud = np.exp(r_lm) > 1e-3
+    np.testing.assert_allclose(lm[loud], r_lm[loud], rtol=1e-4, atol=1e-4)
+
+
+# --------------------------------------------------------------------------- K5-K7
+@pytest.mark.parametrize("arch", [195, 106])
+def test_forward_fp32(engine, arch):
+    engine.set_precision("fp32")
+    w = synth.synthetic_weights(arch)
+    engine.load_model(0, arch, w)
+    x = synth.make_clips(10, seed=arch)
+    probs, amax = engine.forward(dev(x), views=((0, 1.0),))
+    ref = network.forward(x, w, arch, dtype=torch.float64)
+    got = probs.cpu().numpy()
+    assert got.shape == ref.shape
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-5)
+    assert np.array_equal(amax.cpu().numpy(), ref.argmax(1))
+
+
+def test_forward_tta_fp32(engine):
+    engine.set_precision("fp32")
+    w = synth.synthetic_weights(195)
+    engine.load_model(0, 195, w)
+    x = synth.make_clips(12, seed=9)
+    for views in (TTA_SHIPPED, TTA_8):
+        probs, amax = engine.forward(dev(x), views=views)
+        r_probs, r_pred = driver.tta_predict(lambda v: network.forward(v, w, 195, dtype=torch.float64), x, views)
+        np.testing.assert_allclose(probs.cpu().numpy(), r_probs, rtol=1e-4, atol=1e-5)
+        assert np.array_equal(amax.cpu().numpy(), r_pred)
+
+
+def test_forward_chunking_and_slots(engine):
+    """More clip-views than max_rows (512): internal chunking must not change results; two
+    model slots stay independent."""
+    engine.set_precision("fp32")
+    w195, w206 = synth.synthetic_weights(195), synth.synthetic_weights(206)
+    engine.load_model(0, 195, w195)
+    engine.load_model(1, 206, w206)
+    x = synth.make_clips(150, seed=10)
+    xt = dev(x)
+    p_all, _ = engine.forward(xt, views=TTA_8, slot=0)
+    p_head, _ = engine.forward(xt[:20], views=TTA_8, slot=0)
+    assert torch.equal(p_all[:20], p_head)
+    p1, _ = engine.forward(xt[:8], slot=1)
+    np.testing.assert_allclose(p1.cpu().numpy(), network.forward(x[:8], w206, 206, dtype=torch.float64),
+                               rtol=1e-4, atol=1e-5)
+
+
+# --------------------------------------------------------------------------- K8
+def test_select_vote_against_fixtures(engine, driver_fixtures):
+    """Full-size (158,538 clips) integer paths, bit-exact against the reference's fixtures."""
+    p = driver_fixtures["probs_u8"]
+    pt = dev(p)
+    for thr, dropped in ((0.7, 12699), (0.6, 6936)):
+        label, keep = engine.select(pt, thr)
+        r_label, r_keep = driver.threshold_select(p, thr)
+        assert np.array_equal(label.cpu().numpy(), r_label)
+        assert np.array_equal(keep.cpu().numpy().astype(bool), r_keep)
+        assert int((~keep.bool()).sum()) == dropped
+    codes = driver_fixtures["sub_codes"].astype(np.int32)
+    ct = dev(codes)
+    for mc in (2, 3):
+        voted, clear = engine.vote(ct, mc)
+        assert np.array_equal(voted.cpu().numpy(), driver_fixtures[f"ka_vote{mc}_labels"])
+        assert int(clear.sum()) == int(driver_fixtures[f"ka_vote{mc}_clear"])
+    _, un = engine.vote(ct, 3)
+    assert int(un.sum()) == 140945
+
+
+def test_vote_tie_rule_gpu(engine):
+    rs = np.random.RandomState(3)
+    labels = rs.randint(0, 4, (5, 4000)).astype(np.int32)
+    for mc in (2, 3, 4):
+        voted, clear = engine.vote(dev(labels), mc)
+        r_voted, r_clear = driver.majority_vote(labels, mc)
+        assert np.array_equal(voted.cpu().numpy(), r_voted)
+        assert np.array_equal(clear.cpu().numpy().astype(bool), r_clear)
+
+
+def test_convert_32_to_12(engine):
+    rs = np.random.RandomState(0)
+    p = rs.dirichlet(np.ones(32) * 0.2, size=5000).astype(np.float32)
+    for order in ("heng", "frozen"):
+        out, u8 = engine.convert_classes(dev(p), class_map_32_to_12(order), 12)
+        r_sm, r_u8 = driver.convert_32_to_12(p, order)
+        np.testing.assert_allclose(out.cpu().numpy(), r_sm, rtol=2e-6, atol=1e-7)
+        d = np.abs(u8.cpu().numpy().astype(int) - r_u8.astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 1e-3          # trunc(p*255) at a 1-ulp knife edge
+        assert np.array_equal(u8.cpu().numpy().argmax(1), r_u8.argmax(1)) or (d > 0).any()
+
+
+# --------------------------------------------------------------------------- host entry points
+def test_host_entry_points(engine, synth_small):
+    engine.set_precision("fp32")
+    w = synth.synthetic_weights(195)
+    engine.load_model(0, 195, w)
+    engine.frontend_config(480, 160, 40, 40)
+    bank, offs = synth_small["bank"], synth_small["offsets"]
+    engine.set_noise_bank(dev(bank), offs)
+    B = 37
+    x = synth.make_clips(B, seed=55)
+    p = synth.make_params(B, offs, seed=56)
+    bg = augment.gather_background(bank, offs, p["bg_index"], p["bg_offset"])
+    r_aug = augment.augment_mix(x, p["time_shift"], bg, p["bg_volume"], p["fg_volume"])
+    raw = engine.get_data_host(x, p["time_shift"], p["bg_index"], p["bg_offset"], p["bg_volume"],
+                               p["fg_volume"], kind="raw")
+    assert np.array_equal(raw, r_aug)
+    mf = engine.get_data_host(x, p["time_shift"], p["bg_index"], p["bg_offset"], p["bg_volume"],
+                              p["fg_volume"], kind="mfcc")
+    assert rel_err(mf.reshape(B, 98, 40), frontend.features(r_aug, kind="mfcc")) < 1e-4
+    probs, amax = engine.predict_host(x, views=TTA_SHIPPED)
+    r_probs, r_pred = driver.tta_predict(lambda v: network.forward(v, w, 195, dtype=torch.float64), x, TTA_SHIPPED)
+    np.testing.assert_allclose(probs, r_probs, rtol=1e-4, atol=1e-5)
+    assert np.array_equal(amax, r_pred)
+    feat = np.empty((B, 98 * 40), np.float32)
+    pr = np.empty((B, 12), np.float32)
+    am = np.empty((B,), np.int32)
+    engine.pipeline_host(x, p, feat_kind="logmel", views=TTA_8, feat_out=feat, probs_out=pr, argmax_out=am)
+    assert rel_err(feat.reshape(B, 98, 40), frontend.features(r_aug, kind="logmel")) < 1e-4
+    r_probs, r_pred = driver.tta_predict(lambda v: network.forward(v, w, 195, dtype=torch.float64), r_aug, TTA_8)
+    np.testing.assert_allclose(pr, r_probs, rtol=1e-4, atol=1e-5)
+    assert np.array_equal(am, r_pred)

@@ -1,0 +1,181 @@
+"""CPU tests of the oracle (checker) against independent implementations and of the
+host-side logic that mirrors the reference's parameter draw."""
+import numpy as np
+import pytest
+import torch
+from hypothesis import given, settings, strategies as st
+
+from oracle import augment, frontend, network, driver
+from speech_recognition_b200 import arch as parch, synth
+from speech_recognition_b200.audio_processor import draw_augmentation_params
+from speech_recognition_b200.model_settings import prepare_model_settings
+
+
+@given(st.integers(-40000, 40000))
+@settings(max_examples=200, deadline=None)
+def test_tf_roll_is_np_roll(shift):
+    # input_data.py:345 "TODO(see--): Write test with np.roll"
+    x = np.arange(16000, dtype=np.float32)
+    assert np.array_equal(augment.tf_roll(x, shift), np.roll(x, shift))
+
+
+def test_augment_mix_separate_roundings():
+    rs = np.random.RandomState(0)
+    wav = rs.randn(4, 16000).astype(np.float32)
+    bg = rs.randn(4, 16000).astype(np.float32)
+    fv = np.array([1.0, 0.9, 1.13, 0.0], np.float32)
+    bv = np.array([0.0, 0.1, 0.07, 0.3], np.float32)
+    sh = np.array([0, -500, 77, 16000], np.int32)
+    out = augment.augment_mix(wav, sh, bg, bv, fv)
+    for b in range(4):
+        ref = np.float32(bg[b] * bv[b]) + np.roll(np.float32(wav[b] * fv[b]), sh[b])
+        assert np.array_equal(out[b], ref.astype(np.float32))
+    assert out.dtype == np.float32
+
+
+def test_same_pad_rules():
+    # (1,1) for T=397,197,97,47 and (0,1) for T=22; patches pad (10,10)
+    for T in (397, 197, 97, 47):
+        assert network.same_pad(T, 3, 2)[1:] == (1, 1)
+    assert network.same_pad(22, 3, 2) == (11, 0, 1)
+    assert network.same_pad(16000, 40, 20) == (800, 10, 10)
+    assert network.layer_lengths(195) == [800, 399, 397, 199, 197, 99, 97, 49, 47, 24, 22, 11, 9]
+    assert parch.layer_lengths(106) == network.layer_lengths(106)
+    assert parch.weight_shapes(195) == network.weight_shapes(195)
+    assert sum(int(np.prod(s)) for s in network.weight_shapes(195).values()) == 1198601
+    assert sum(int(np.prod(s)) for s in network.weight_shapes(106).values()) == 1092416
+
+
+def test_spectrogram_matches_torch_fft():
+    x = synth.make_clips(3, seed=11)
+    ours = frontend.spectrogram(x)
+    w = torch.tensor(frontend.hann_window_periodic(480))
+    fr = torch.tensor(x).unfold(1, 480, 160) * w
+    ref = torch.fft.rfft(torch.nn.functional.pad(fr, (0, 32)).double(), dim=-1).abs().float().numpy()
+    assert ours.shape == (3, 98, 257)
+    np.testing.assert_allclose(ours, ref, rtol=1e-6, atol=1e-6)
+    # hann: torch's periodic window is the same function
+    np.testing.assert_allclose(frontend.hann_window_periodic(480), torch.hann_window(480, periodic=True).numpy(),
+                               atol=5e-7)
+
+
+def test_mel_matrix_properties():
+    for M in (40, 80):
+        W = frontend.linear_to_mel_weight_matrix(M)
+        assert W.shape == (257, M) and W.dtype == np.float32
+        assert (W[0] == 0).all()                      # DC row is the zero pad
+        assert ((W > 0).sum(axis=1) <= 2).all()       # triangular filters overlap pairwise
+    assert (frontend.linear_to_mel_weight_matrix(40) > 0).sum() == 465
+    assert (frontend.linear_to_mel_weight_matrix(80) > 0).sum() == 473
+
+
+def test_mfcc_is_scaled_dct2():
+    import scipy.fft
+    rs = np.random.RandomState(1)
+    lm = rs.randn(2, 98, 40).astype(np.float32)
+    ours = frontend.mfcc_from_log_mel(lm)
+    ref = scipy.fft.dct(lm.astype(np.float64), type=2, axis=-1) / np.sqrt(2 * 40)
+    np.testing.assert_allclose(ours, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_network_matches_naive_loops():
+    """The torch-op restatement against literal loops for the first layers and the head."""
+    w = synth.synthetic_weights(195)
+    x = synth.make_clips(2, seed=3)
+    probs, logits, acts = network.forward(x, w, 195, dtype=torch.float64, return_activations=True)
+    # conv1d_1 at a few positions: y[j,co] = sum_{f,i} P[2j+f,i] W[f,i,co], P[j,i] = x[20j-10+i]
+    k = w["conv1d_1/kernel"].astype(np.float64)
+    xp = np.pad(x[0].astype(np.float64), (10, 10))
+    s = w["batch_normalization_1/gamma"] / np.sqrt(w["batch_normalization_1/moving_variance"].astype(np.float64) + 1e-3)
+    sh = w["batch_normalization_1/beta"] - w["batch_normalization_1/moving_mean"] * s
+    for j in (0, 1, 200, 398):
+        acc = np.zeros(128)
+        for f in range(3):
+            patch = xp[20 * (2 * j + f): 20 * (2 * j + f) + 40]
+            acc += patch @ k[f]
+        ref = np.clip(acc * s + sh, 0, 6)
+        np.testing.assert_allclose(acts[0][0, j], ref, rtol=1e-9, atol=1e-9)
+    # block 2 (stride 2, SAME pad (1,1)) at the edges
+    a_in = acts[1][0]                                   # [397,128]
+    dk = w["depthwise_conv2d_2/depthwise_kernel"][0, :, :, 0].astype(np.float64)
+    pk = w["conv1d_3/kernel"][0].astype(np.float64)
+    s = w["batch_normalization_3/gamma"] / np.sqrt(w["batch_normalization_3/moving_variance"].astype(np.float64) + 1e-3)
+    sh = w["batch_normalization_3/beta"] - w["batch_normalization_3/moving_mean"] * s
+    for t in (0, 1, 198):
+        d = np.zeros(128)
+        for j in range(3):
+            ti = 2 * t + j - 1
+            if 0 <= ti < 397:
+                d += dk[j] * a_in[ti]
+        ref = np.clip((d @ pk) * s + sh, 0, 6)
+        np.testing.assert_allclose(acts[2][0, t], ref, rtol=1e-9, atol=1e-9)
+    # head
+    xl = acts[-1][0]                                    # [9,512]
+    att = xl.reshape(-1) @ w["dense_1/kernel"].astype(np.float64) + w["dense_1/bias"]
+    att = np.exp(att - att.max()); att /= att.sum()
+    z = np.concatenate([(xl * att[:, None]).max(0), xl.mean(0)])
+    lg = z @ w["dense_2/kernel"].astype(np.float64)
+    np.testing.assert_allclose(logits[0], lg, rtol=1e-9, atol=1e-9)
+    assert probs.shape == (2, 12)
+
+
+def test_network_106_shapes():
+    w = synth.synthetic_weights(106)
+    p = network.forward(synth.make_clips(2, seed=4), w, 106)
+    assert p.shape == (2, 32)
+    np.testing.assert_allclose(p.sum(1), 1.0, atol=1e-5)
+
+
+def test_draw_order_matches_product_host_code():
+    """oracle.draw_params (checker) and AudioProcessor's draw (product host logic) are two
+    restatements of input_data.py:457-514: same seed -> same parameters, bit for bit."""
+    ms = prepare_model_settings(12, 16000, 1000, 30.0, 10.0, 40, 40, 'raw')
+    n = 200
+    labels = np.arange(n) % 12                      # label 0 = silence
+    pseudo_labels = (np.arange(50) * 7) % 12
+    clips = np.zeros((n, 1), np.float32)
+    bgs = [np.zeros(40000, np.float32), np.zeros(70000, np.float32), np.zeros(16500, np.float32)]
+    kw = dict(background_frequency=0.3, background_volume_range=0.15, foreground_frequency=0.3,
+              foreground_volume_range=0.15, time_shift_frequency=0.3, time_shift_range=[-500, 0],
+              pseudo_frequency=0.33, flip_frequency=0.2, silence_volume_range=0.3)
+    for mode in ("training", "validation"):
+        rs = np.random.RandomState(123)
+        ref = augment.draw_params(rs, how_many=64, offset=8, n_candidates=n, candidate_is_silence=labels == 0,
+                                  mode=mode, background_lengths=[len(b) for b in bgs], n_pseudo=50,
+                                  pseudo_is_silence=pseudo_labels == 0, **kw)
+        np.random.seed(123)
+        idx, from_pseudo, lab, p = draw_augmentation_params(
+            {mode: (clips, labels), 'pseudo': (np.zeros((50, 1), np.float32), pseudo_labels)}, bgs, ms,
+            64, 8, kw['background_frequency'], kw['background_volume_range'], kw['foreground_frequency'],
+            kw['foreground_volume_range'], kw['time_shift_frequency'], kw['time_shift_range'], mode,
+            kw['pseudo_frequency'], kw['flip_frequency'], kw['silence_volume_range'])
+        assert np.array_equal(idx, ref['sample_index'])
+        assert np.array_equal(from_pseudo, ref['from_pseudo'])
+        for k_ref, k_p in (('time_shift', 'time_shift'), ('bg_index', 'bg_index'), ('bg_offset', 'bg_offset'),
+                           ('bg_volume', 'bg_volume'), ('fg_volume', 'fg_volume')):
+            assert np.array_equal(ref[k_ref], p[k_p]), (mode, k_ref)
+        if mode == "training":
+            assert (ref['time_shift'] <= 0).all() and (ref['time_shift'] >= -500).all()
+            assert (p['fg_volume'][lab == 0] == 0).all()
+
+
+def test_model_settings():
+    ms = prepare_model_settings(12, 16000, 1000, 30.0, 10.0, 40, 40, 'mfcc')
+    assert ms['spectrogram_length'] == 98 and ms['fingerprint_size'] == 3920     # settings.py:1-11
+    ms = prepare_model_settings(32, 16000, 1000, 25.0, 15.0, 80, 60, 'raw')      # make_submission.py:53-57
+    assert ms['window_size_samples'] == 400 and ms['window_stride_samples'] == 240
+    assert ms['fingerprint_size'] == 16000
+
+
+def test_tta_predict_order():
+    calls = []
+
+    def predict(x):
+        calls.append(x.copy())
+        return np.tile(np.arange(3, dtype=np.float32)[None] * (len(calls)), (len(x), 1))
+    x = np.random.RandomState(0).randn(2, 16000).astype(np.float32)
+    probs, pred = driver.tta_predict(predict, x, driver.TTA_SHIPPED)
+    assert np.array_equal(calls[0], x)
+    assert np.array_equal(calls[1], (np.float32(1.2) * x).astype(np.float32))     # loud
+    assert np.array_equal(calls[2], np.roll(x, -1500, axis=1))                    # left
+    assert np.array_equal(pred, [2, 2])
