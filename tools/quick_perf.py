@@ -37,7 +37,7 @@ print(f"augment   B={B}: {t:.3f} ms  {B/t*1e3:.0f} clips/s  {B*192020/t/1e6:.1f}
 for kind in ("spec", "logmel", "mfcc"):
     t = timeit(lambda: eng.features(aug, kind))
     print(f"features[{kind}] {prec}: {t:.3f} ms  {B/t*1e3:.0f} clips/s  {B*50.7e6/t/1e9:.1f} TFLOP/s-equiv")
-for views, name in (((0, 1.0),), "1 view"), (TTA_8, "8 views")):
+for views, name in ((((0, 1.0),), "1 view"), (TTA_8, "8 views")):
     t = timeit(lambda: eng.forward(aug, views=views), n=3, warm=1)
     nv = len(views)
     print(f"forward[{name}] {prec}: {t:.3f} ms  {B/t*1e3:.0f} clips/s  {B*nv*112.48e6/t/1e9:.1f} TFLOP/s")
