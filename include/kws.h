@@ -114,6 +114,11 @@ int kws_forward(kws_t* h, int slot, const float* wav, int B, const int32_t* view
                 const float* view_gain_h, int n_views, float* probs_mean, int32_t* argmax,
                 void* stream);
 
+/* Parity aid: run the network up to `layer` (0 = conv1d_1+BN+ReLU6, i = block i, 1..11) and
+ * write that activation as fp32 [B*n_views, T_layer, C_layer] (needs B*n_views <= max_rows). */
+int kws_debug_activation(kws_t* h, int slot, const float* wav, int B, const int32_t* view_shift_h,
+                         const float* view_gain_h, int n_views, int layer, float* out, void* stream);
+
 /* ---- driver math on the device ---- */
 /* 32 -> 12 conversion (convert_from_see_v3_bugfix.py:76-110, freeze_graph_32_classes.py:55-69):
  * out[j] = max_{c: class_map[c]==j} p[c]; re-softmax exp(x)/sum (no max subtraction);

@@ -40,6 +40,7 @@ SIGNATURES = {
     "kws_model_load": (_i, [_vp, _i, _i, C.POINTER(TensorH), _i]),
     "kws_model_classes": (_i, [_vp, _i]),
     "kws_forward": (_i, [_vp, _i, _vp, _i, C.POINTER(C.c_int32), C.POINTER(_f), _i, _vp, _vp, _vp]),
+    "kws_debug_activation": (_i, [_vp, _i, _vp, _i, C.POINTER(C.c_int32), C.POINTER(_f), _i, _i, _vp, _vp]),
     "kws_convert_classes": (_i, [_vp, _vp, _i, _i, C.POINTER(C.c_int32), _i, _vp, _vp, _vp]),
     "kws_select": (_i, [_vp, _vp, _i, _i, _d, _vp, _vp, _vp]),
     "kws_vote": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),

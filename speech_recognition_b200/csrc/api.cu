@@ -210,6 +210,21 @@ int kws_forward(kws_t* h, int slot, const float* wav, int B, const int32_t* view
   return forward_dispatch(h, slot, wav, B, vt, probs_mean, argmax, static_cast<cudaStream_t>(stream));
 }
 
+int kws_debug_activation(kws_t* h, int slot, const float* wav, int B, const int32_t* view_shift_h,
+                         const float* view_gain_h, int n_views, int layer, float* out, void* stream) {
+  if (!h) return KWS_EINVAL;
+  ViewTable vt;
+  int rc = make_views(h, view_shift_h, view_gain_h, n_views, &vt);
+  if (rc) return rc;
+  if (slot < 0 || slot >= KWS_MAX_MODELS || !h->models[slot].loaded) return fail(h, KWS_ESTATE, "model not loaded");
+  if (layer < 0 || layer > NUM_BLOCKS || !out || !wav || B <= 0) return fail(h, KWS_EINVAL, "bad arguments");
+  if (B * n_views > h->max_rows) return fail(h, KWS_EINVAL, "debug activation needs B*n_views <= max_rows");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return h->precision == KWS_PREC_FP32
+             ? launch_forward_f32(h, h->models[slot], wav, B, vt, nullptr, nullptr, st, layer, out)
+             : launch_forward_tc(h, h->models[slot], wav, B, vt, nullptr, nullptr, st, layer, out);
+}
+
 int kws_convert_classes(kws_t* h, const float* probs, int B, int C_in, const int32_t* class_map_h,
                         int C_out, float* probs_out, uint8_t* probs_u8, void* stream) {
   if (!h) return KWS_EINVAL;

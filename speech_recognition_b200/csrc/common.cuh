@@ -40,10 +40,10 @@ struct Model {
   float* w_d1 = nullptr;                  // [t_last*c_last, t_last]
   float* b_d1 = nullptr;                  // [t_last] (zeros when the arch has no bias)
   float* w_d2 = nullptr;                  // [feat, classes]
-  // tensor-core operand images (bf16, pre-swizzled UMMA K-major SW128 slabs)
+  // tensor-core operand images (fp16, pre-swizzled UMMA K-major SW128 slabs)
   void* tc_blob = nullptr;
-  __nv_bfloat16* tc_conv1 = nullptr;      // [kblocks][c0 rows][64] swizzled
-  __nv_bfloat16* tc_pw[NUM_BLOCKS];       // [kblocks][cout rows][64] swizzled
+  __half* tc_conv1 = nullptr;             // [2 slabs][c0 rows][64] swizzled, 80 folded taps
+  __half* tc_pw[NUM_BLOCKS];              // [cin/64 slabs][cout rows][64] swizzled
   size_t max_act_elems = 0;               // max over layers of T*C (per clip-view)
 };
 
@@ -123,11 +123,16 @@ int frontend_build(kws_handle* h, int win, int hop, int n_mel, int n_keep, float
 int launch_features_f32(kws_handle* h, const float* wav, int B, int kind, float* out, cudaStream_t st);
 int launch_features_tc(kws_handle* h, const float* wav, int B, int kind, float* out, cudaStream_t st);
 int model_build(kws_handle* h, int slot, int arch, const kws_tensor_h* t, int n);
+// dbg_layer >= 0: stop after layer dbg_layer (0 = conv1d_1, i = block i) of the FIRST chunk and
+// write that activation as fp32 [rows, T, C] to dbg_out (development / parity aid).
 int launch_forward_f32(kws_handle* h, Model& m, const float* wav, int B, const ViewTable& vt,
-                       float* probs_mean, int32_t* argmax, cudaStream_t st);
+                       float* probs_mean, int32_t* argmax, cudaStream_t st, int dbg_layer = -1,
+                       float* dbg_out = nullptr);
 int launch_forward_tc(kws_handle* h, Model& m, const float* wav, int B, const ViewTable& vt,
-                      float* probs_mean, int32_t* argmax, cudaStream_t st);
-int launch_head(kws_handle* h, Model& m, const void* act, bool act_bf16, int n_clips, int n_views,
+                      float* probs_mean, int32_t* argmax, cudaStream_t st, int dbg_layer = -1,
+                      float* dbg_out = nullptr);
+int launch_to_float(kws_handle* h, const void* src, bool src_half, float* dst, size_t n, cudaStream_t st);
+int launch_head(kws_handle* h, Model& m, const void* act, bool act_half, int n_clips, int n_views,
                 float* probs_mean, int32_t* argmax, cudaStream_t st);
 int launch_convert(kws_handle* h, const float* probs, int B, int C_in, const int32_t* class_map_h,
                    int C_out, float* probs_out, uint8_t* probs_u8, cudaStream_t st);

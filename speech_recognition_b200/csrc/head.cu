@@ -6,6 +6,8 @@
 // and across views (make_submission.py:137-146): probs = (p_0 + p_1 + ...) / n_views in view
 // order, argmax with first-index tie rule.  Memory/latency-bound CUDA-core work with
 // warp-shuffle reductions; the weights (166 KB + 48 KB) stay L2/L1-resident.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace kws {
@@ -17,7 +19,7 @@ constexpr int HEAD_T = 9;                 // time steps entering the head (both 
 constexpr int HEAD_MAX_CLASSES = 32;
 
 __device__ __forceinline__ float to_float(float v) { return v; }
-__device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_float(__half v) { return __half2float(v); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -130,16 +132,34 @@ head_kernel(const TAct* __restrict__ act, int C, int n_views, const float* __res
 
 }  // namespace
 
-int launch_head(kws_handle* h, Model& m, const void* act, bool act_bf16, int n_clips, int n_views,
+namespace {
+template <typename T>
+__global__ void to_float_kernel(const T* __restrict__ src, float* __restrict__ dst, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    dst[i] = to_float(src[i]);
+}
+}  // namespace
+
+int launch_to_float(kws_handle* h, const void* src, bool src_half, float* dst, size_t n, cudaStream_t st) {
+  if (n == 0) return KWS_OK;
+  const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, 4096));
+  if (src_half) to_float_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(src), dst, n);
+  else to_float_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(src), dst, n);
+  KWS_LAUNCH_CHECK(h);
+  return KWS_OK;
+}
+
+int launch_head(kws_handle* h, Model& m, const void* act, bool act_half, int n_clips, int n_views,
                 float* probs_mean, int32_t* argmax, cudaStream_t st) {
   if (m.t_last != HEAD_T) return fail(h, KWS_EUNSUPPORTED, "head expects 9 time steps");
   if (m.classes > HEAD_MAX_CLASSES) return fail(h, KWS_EUNSUPPORTED, "too many classes");
   const int C = m.c_last;
   const size_t smem = (static_cast<size_t>(HEAD_T) * C + 2 * C + (HEAD_THREADS / 32) * HEAD_T + 16 +
                        HEAD_MAX_CLASSES) * sizeof(float);
-  if (act_bf16) {
-    head_kernel<__nv_bfloat16><<<n_clips, HEAD_THREADS, smem, st>>>(
-        static_cast<const __nv_bfloat16*>(act), C, n_views, m.w_d1, m.b_d1, m.w_d2, m.classes,
+  if (act_half) {
+    head_kernel<__half><<<n_clips, HEAD_THREADS, smem, st>>>(
+        static_cast<const __half*>(act), C, n_views, m.w_d1, m.b_d1, m.w_d2, m.classes,
         m.pool_max_avg ? 1 : 0, probs_mean, argmax);
   } else {
     head_kernel<float><<<n_clips, HEAD_THREADS, smem, st>>>(

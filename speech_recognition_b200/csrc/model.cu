@@ -11,8 +11,8 @@
 
 namespace kws {
 
-int model_build_tc(kws_handle* h, Model& m, const std::vector<std::vector<float>>& pw_scaled,
-                   const std::vector<float>& conv1_scaled);   // tc_net.cu
+int model_build_tc(kws_handle* h, Model& m, const std::vector<std::vector<float>>& pw_host,
+                   const std::vector<float>& conv1_host);   // tc_net.cu
 
 namespace {
 
@@ -135,19 +135,8 @@ int model_build(kws_handle* h, int slot, int arch, const kws_tensor_h* t, int n)
   for (int i = 0; i < NUM_BLOCKS; ++i) { m.w_dw[i] = m.blob + o_dw[i]; m.w_pw[i] = m.blob + o_pw[i]; }
   m.w_d1 = m.blob + o_d1; m.b_d1 = m.blob + o_b1; m.w_d2 = m.blob + o_d2;
 
-  // tensor-core operand images: BN scale folded into the bf16 weights (W' = W * s per output channel)
-  std::vector<std::vector<float>> pw_scaled(NUM_BLOCKS);
-  for (int i = 0; i < NUM_BLOCKS; ++i) {
-    const LayerDesc& d = m.layers[i];
-    pw_scaled[i].resize(pw_host[i].size());
-    for (int k = 0; k < d.cin; ++k)
-      for (int c = 0; c < d.cout; ++c)
-        pw_scaled[i][static_cast<size_t>(k) * d.cout + c] = pw_host[i][static_cast<size_t>(k) * d.cout + c] * scales[i + 1][c];
-  }
-  std::vector<float> conv1_scaled(conv1_host.size());
-  for (int k = 0; k < 120; ++k)
-    for (int c = 0; c < m.c0; ++c) conv1_scaled[k * m.c0 + c] = conv1_host[k * m.c0 + c] * scales[0][c];
-  if ((rc = model_build_tc(h, m, pw_scaled, conv1_scaled))) return rc;
+  // tensor-core operand images (fp16, pre-swizzled); BN scale/shift stay fp32 in the epilogue
+  if ((rc = model_build_tc(h, m, pw_host, conv1_host))) return rc;
   m.loaded = true;
   return KWS_OK;
 }
@@ -158,7 +147,7 @@ int model_build(kws_handle* h, int slot, int arch, const kws_tensor_h* t, int n)
 // handle's workspace; rows = clips_in_chunk * n_views, views of a clip adjacent.
 // ---------------------------------------------------------------------------------------------
 int launch_forward_f32(kws_handle* h, Model& m, const float* wav, int B, const ViewTable& vt,
-                       float* probs_mean, int32_t* argmax, cudaStream_t st) {
+                       float* probs_mean, int32_t* argmax, cudaStream_t st, int dbg_layer, float* dbg_out) {
   const int V = vt.n;
   const int clips_per_chunk = std::max(1, h->max_rows / V);
   const size_t need = static_cast<size_t>(clips_per_chunk) * V * m.max_act_elems * sizeof(float);
@@ -183,6 +172,7 @@ int launch_forward_f32(kws_handle* h, Model& m, const float* wav, int B, const V
       launch_gemm_f32(a, m.w_conv1, rows * m.t0, m.c0, 120, e, st);
       KWS_LAUNCH_CHECK(h);
     }
+    if (dbg_layer == 0) return launch_to_float(h, cur, false, dbg_out, static_cast<size_t>(rows) * m.t0 * m.c0, st);
     for (int i = 0; i < NUM_BLOCKS; ++i) {
       const LayerDesc& d = m.layers[i];
       LoadDepthwise a{cur, m.w_dw[i], d.t_in, d.t_out, d.cin, d.stride, d.pad_left};
@@ -190,8 +180,10 @@ int launch_forward_f32(kws_handle* h, Model& m, const float* wav, int B, const V
       launch_gemm_f32(a, m.w_pw[i], rows * d.t_out, d.cout, d.cin, e, st);
       KWS_LAUNCH_CHECK(h);
       std::swap(cur, nxt);
+      if (dbg_layer == i + 1)
+        return launch_to_float(h, cur, false, dbg_out, static_cast<size_t>(rows) * d.t_out * d.cout, st);
     }
-    int rc = launch_head(h, m, cur, /*act_bf16=*/false, nb, V,
+    int rc = launch_head(h, m, cur, /*act_half=*/false, nb, V,
                          probs_mean ? probs_mean + static_cast<size_t>(b0) * m.classes : nullptr,
                          argmax ? argmax + b0 : nullptr, st);
     if (rc) return rc;

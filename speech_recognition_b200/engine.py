@@ -147,6 +147,16 @@ class Engine:
                                          self._dp(amax), self._stream()))
         return probs, amax
 
+    def debug_activation(self, wav_t, layer: int, shape, views=((0, 1.0),), slot=0):
+        """fp32 activation after `layer` (0 = conv1d_1, i = block i); shape = (T, C) of that layer."""
+        import torch
+        B = wav_t.shape[0]
+        sh, ga, n = _views(views)
+        out = torch.empty((B * n, shape[0], shape[1]), dtype=torch.float32, device=wav_t.device)
+        self._check(self.lib.kws_debug_activation(self.h, slot, self._dp(wav_t), B, sh, ga, n, int(layer),
+                                                  self._dp(out), self._stream()))
+        return out
+
     # -- driver math --
     def convert_classes(self, probs_t, class_map, n_out=12):
         import torch

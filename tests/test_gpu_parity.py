@@ -238,3 +238,46 @@ def test_host_entry_points(engine, synth_small):
     r_probs, r_pred = driver.tta_predict(lambda v: network.forward(v, w, 195, dtype=torch.float64), r_aug, TTA_8)
     np.testing.assert_allclose(pr, r_probs, rtol=1e-4, atol=1e-5)
     assert np.array_equal(am, r_pred)
+
+
+# --------------------------------------------------------------------------- tensor-core tier
+@pytest.mark.parametrize("arch", [195, 106])
+def test_forward_tc_layers(engine, arch):
+    """tcgen05 tier layer by layer against the oracle's activations (fp16 operands, fp32 accumulate)."""
+    from speech_recognition_b200 import arch as A
+    w = synth.synthetic_weights(arch)
+    engine.load_model(0, arch, w)
+    x = synth.make_clips(4, seed=300 + arch)
+    _, _, acts = network.forward(x, w, arch, dtype=torch.float64, return_activations=True)
+    engine.set_precision("tc")
+    try:
+        Ts = A.layer_lengths(arch)[1:]
+        for layer in (0, 1, 2, 5, 8, 11):
+            got = engine.debug_activation(dev(x), layer, (Ts[layer], acts[layer].shape[2])).cpu().numpy()
+            ref = acts[layer]
+            assert got.shape == ref.shape
+            err = np.abs(got - ref)
+            # activations live in [0, 6]; 1e-2 tier, absolute (fp16 storage alone is 6 * 2^-11 = 3e-3)
+            assert err.max() < 3e-2 and err.mean() < 2e-3, (layer, err.max(), err.mean())
+    finally:
+        engine.set_precision("fp32")
+
+
+@pytest.mark.parametrize("arch,views", [(195, TTA_SHIPPED), (195, TTA_8), (106, TTA_SHIPPED)])
+def test_forward_tc(engine, arch, views):
+    w = synth.synthetic_weights(arch)
+    engine.load_model(0, arch, w)
+    x = synth.make_clips(96, seed=400 + arch)
+    engine.set_precision("tc")
+    try:
+        probs, amax = engine.forward(dev(x), views=views)
+    finally:
+        engine.set_precision("fp32")
+    r_probs, r_pred = driver.tta_predict(lambda v: network.forward(v, w, arch, dtype=torch.float64), x, views)
+    got = probs.cpu().numpy()
+    assert np.abs(got - r_probs).max() < 1e-2                      # 1e-2 tier on probabilities
+    agree = (amax.cpu().numpy() == r_pred).mean()
+    margin = np.sort(r_probs, axis=1)
+    confident = (margin[:, -1] - margin[:, -2]) > 2e-2             # labels may only flip on near-ties
+    assert (amax.cpu().numpy()[confident] == r_pred[confident]).all()
+    assert agree >= 0.97
