@@ -76,6 +76,13 @@ int  kws_set_precision(kws_t* h, int precision);          /* KWS_PREC_*  (defaul
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t kws_launch_count(const kws_t* h);
 
+/* Per-kernel-class device timing for roofline reports: when enabled every launch is bracketed
+ * by CUDA events on its stream; kws_timing_read() synchronises, sums the elapsed milliseconds
+ * and launch counts per class and resets.  Classes: 0 augment, 1 DFT/STFT GEMM, 2 mel+DCT,
+ * 3 slice_conv1, 4 depthwise+pointwise blocks, 5 head, 6 other (n_classes >= 7). */
+int kws_timing_enable(kws_t* h, int on);
+int kws_timing_read(kws_t* h, double* ms_per_class, int64_t* count_per_class, int n_classes);
+
 /* ---- stage 1a: waveform augmentation  (input_data.py:338-359, utils.py:56-73) ---- */
 /* background_data list of AudioProcessor (input_data.py:274-309) as one concatenated
  * device array; file_offsets_h[n_files+1] are the start indices of each wav. */

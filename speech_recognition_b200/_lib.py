@@ -31,6 +31,8 @@ SIGNATURES = {
     "kws_last_error": (C.c_char_p, [_vp]),
     "kws_set_precision": (_i, [_vp, _i]),
     "kws_launch_count": (_i64, [_vp]),
+    "kws_timing_enable": (_i, [_vp, _i]),
+    "kws_timing_read": (_i, [_vp, C.POINTER(_d), C.POINTER(_i64), _i]),
     "kws_set_noise_bank": (_i, [_vp, _vp, C.POINTER(_i64), _i]),
     "kws_augment": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "kws_augment_pcm16": (_i, [_vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),

@@ -29,6 +29,19 @@ int ensure_bytes(kws_handle* h, void** p, size_t* cur, size_t need, bool pinned)
   return KWS_OK;
 }
 
+void timer_begin(kws_handle* h, int cls, cudaStream_t st) {
+  auto get = [&]() {
+    cudaEvent_t e;
+    if (!h->event_pool.empty()) { e = h->event_pool.back(); h->event_pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+  };
+  kws_handle::TimedLaunch t{cls, get(), get()};
+  cudaEventRecord(t.e0, st);
+  h->timed.push_back(t);
+}
+void timer_end(kws_handle* h, cudaStream_t st) { cudaEventRecord(h->timed.back().e1, st); }
+
 static int make_views(kws_handle* h, const int32_t* shift_h, const float* gain_h, int n, ViewTable* vt) {
   if (n <= 0 || n > KWS_MAX_VIEWS) return fail(h, KWS_EINVAL, "n_views must be in 1..16");
   vt->n = n;
@@ -121,7 +134,30 @@ void kws_destroy(kws_t* h) {
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->stage_d) cudaFree(h->stage_d);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  for (auto& t : h->timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+  for (auto e : h->event_pool) cudaEventDestroy(e);
   delete h;
+}
+
+int kws_timing_enable(kws_t* h, int on) {
+  if (!h) return KWS_EINVAL;
+  h->timing = on != 0;
+  return KWS_OK;
+}
+
+int kws_timing_read(kws_t* h, double* ms_per_class, int64_t* count_per_class, int n_classes) {
+  if (!h) return KWS_EINVAL;
+  if (n_classes < KC_COUNT || !ms_per_class || !count_per_class) return fail(h, KWS_EINVAL, "need 7 class slots");
+  for (int i = 0; i < n_classes; ++i) { ms_per_class[i] = 0.0; count_per_class[i] = 0; }
+  for (auto& t : h->timed) {
+    KWS_CUDA(h, cudaEventSynchronize(t.e1));
+    float ms = 0.f;
+    KWS_CUDA(h, cudaEventElapsedTime(&ms, t.e0, t.e1));
+    ms_per_class[t.cls] += ms; count_per_class[t.cls]++;
+    h->event_pool.push_back(t.e0); h->event_pool.push_back(t.e1);
+  }
+  h->timed.clear();
+  return KWS_OK;
 }
 
 int kws_set_precision(kws_t* h, int precision) {

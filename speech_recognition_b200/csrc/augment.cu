@@ -159,6 +159,7 @@ int launch_augment(kws_handle* h, const float* wav, const int16_t* pcm, float pc
   if (B == 0) return KWS_OK;
   const long long* fo = reinterpret_cast<const long long*>(h->file_offsets_d);
   dim3 grid(static_cast<unsigned>(B) * AUG_TILES), block(AUG_THREADS);
+  KWS_T0(h, KC_AUGMENT, st);
   if (pcm != nullptr) {
     augment_mix_kernel<int16_t><<<grid, block, 0, st>>>(pcm, pcm_scale, shift, bg_file, bg_off, bg_vol,
                                                         fg_vol, h->bank, h->bank_len, fo, h->n_files,
@@ -167,6 +168,7 @@ int launch_augment(kws_handle* h, const float* wav, const int16_t* pcm, float pc
     augment_mix_kernel<float><<<grid, block, 0, st>>>(wav, 1.0f, shift, bg_file, bg_off, bg_vol, fg_vol,
                                                       h->bank, h->bank_len, fo, h->n_files, out, B, clamp);
   }
+  KWS_T1(h, st);
   KWS_LAUNCH_CHECK(h);
   return KWS_OK;
 }

@@ -90,6 +90,11 @@ struct kws_handle {
   void* pinned = nullptr;  size_t pinned_bytes = 0;
   void* stage_d = nullptr; size_t stage_bytes = 0;
   cudaStream_t own_stream = nullptr;
+  // optional per-kernel-class device timing (bench.py roofline): event pairs around launches
+  bool timing = false;
+  struct TimedLaunch { int cls; cudaEvent_t e0, e1; };
+  std::vector<TimedLaunch> timed;
+  std::vector<cudaEvent_t> event_pool;
 };
 
 namespace kws {
@@ -112,6 +117,13 @@ int ensure_bytes(kws_handle* h, void** p, size_t* cur, size_t need, bool pinned 
       return kws::fail((h), KWS_ECUDA, std::string("kernel launch at ") + __FILE__ + ":" + \
                                            std::to_string(__LINE__) + ": " + cudaGetErrorString(_e)); \
   } while (0)
+
+// kernel classes for kws_timing_read
+enum { KC_AUGMENT = 0, KC_DFT = 1, KC_MELDCT = 2, KC_CONV1 = 3, KC_BLOCKS = 4, KC_HEAD = 5, KC_OTHER = 6, KC_COUNT = 7 };
+void timer_begin(kws_handle* h, int cls, cudaStream_t st);
+void timer_end(kws_handle* h, cudaStream_t st);
+#define KWS_T0(h, cls, st) do { if ((h)->timing) kws::timer_begin((h), (cls), (st)); } while (0)
+#define KWS_T1(h, st) do { if ((h)->timing) kws::timer_end((h), (st)); } while (0)
 
 // ---- launchers implemented in the .cu files ----
 int launch_augment(kws_handle* h, const float* wav, const int16_t* pcm, float pcm_scale,

@@ -119,15 +119,21 @@ int launch_features_f32(kws_handle* h, const float* wav, int B, int kind, float*
     const int M = n * fe.frames;
     float* o = out + static_cast<size_t>(b0) * fe.frames * out_dim;
     float* spec = kind == KWS_FEAT_SPEC ? o : h->spec_ws;
+    KWS_T0(h, KC_DFT, st);
     launch_gemm_f32(LoadFrames{wav + static_cast<size_t>(b0) * L, fe.frames, fe.hop}, fe.dft_basis, M,
                     2 * nb, fe.win, EpiMagnitude{spec, nb}, st);
+    KWS_T1(h, st);
     KWS_LAUNCH_CHECK(h);
     if (kind == KWS_FEAT_SPEC) continue;
     float* lm = kind == KWS_FEAT_LOGMEL ? o : h->mel_ws;
+    KWS_T0(h, KC_MELDCT, st);
     launch_gemm_f32(LoadPlain{spec, nb}, fe.mel_w, M, fe.n_mel, nb, EpiLog{lm, fe.n_mel}, st);
+    KWS_T1(h, st);
     KWS_LAUNCH_CHECK(h);
     if (kind == KWS_FEAT_LOGMEL) continue;
+    KWS_T0(h, KC_MELDCT, st);
     launch_gemm_f32(LoadPlain{lm, fe.n_mel}, fe.dct_w, M, fe.n_keep, fe.n_mel, EpiStore{o, fe.n_keep}, st);
+    KWS_T1(h, st);
     KWS_LAUNCH_CHECK(h);
   }
   return KWS_OK;

@@ -157,6 +157,7 @@ int launch_head(kws_handle* h, Model& m, const void* act, bool act_half, int n_c
   const int C = m.c_last;
   const size_t smem = (static_cast<size_t>(HEAD_T) * C + 2 * C + (HEAD_THREADS / 32) * HEAD_T + 16 +
                        HEAD_MAX_CLASSES) * sizeof(float);
+  KWS_T0(h, KC_HEAD, st);
   if (act_half) {
     head_kernel<__half><<<n_clips, HEAD_THREADS, smem, st>>>(
         static_cast<const __half*>(act), C, n_views, m.w_d1, m.b_d1, m.w_d2, m.classes,
@@ -166,6 +167,7 @@ int launch_head(kws_handle* h, Model& m, const void* act, bool act_half, int n_c
         static_cast<const float*>(act), C, n_views, m.w_d1, m.b_d1, m.w_d2, m.classes,
         m.pool_max_avg ? 1 : 0, probs_mean, argmax);
   }
+  KWS_T1(h, st);
   KWS_LAUNCH_CHECK(h);
   return KWS_OK;
 }

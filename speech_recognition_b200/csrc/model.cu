@@ -169,7 +169,9 @@ int launch_forward_f32(kws_handle* h, Model& m, const float* wav, int B, const V
     {
       LoadSliceConv1 a{wav + static_cast<size_t>(b0) * L, m.t0, V, vt};
       EpiBnRelu6 e{cur, m.bn_scale[0], m.bn_shift[0]};
+      KWS_T0(h, KC_CONV1, st);
       launch_gemm_f32(a, m.w_conv1, rows * m.t0, m.c0, 120, e, st);
+      KWS_T1(h, st);
       KWS_LAUNCH_CHECK(h);
     }
     if (dbg_layer == 0) return launch_to_float(h, cur, false, dbg_out, static_cast<size_t>(rows) * m.t0 * m.c0, st);
@@ -177,7 +179,9 @@ int launch_forward_f32(kws_handle* h, Model& m, const float* wav, int B, const V
       const LayerDesc& d = m.layers[i];
       LoadDepthwise a{cur, m.w_dw[i], d.t_in, d.t_out, d.cin, d.stride, d.pad_left};
       EpiBnRelu6 e{nxt, m.bn_scale[i + 1], m.bn_shift[i + 1]};
+      KWS_T0(h, KC_BLOCKS, st);
       launch_gemm_f32(a, m.w_pw[i], rows * d.t_out, d.cout, d.cin, e, st);
+      KWS_T1(h, st);
       KWS_LAUNCH_CHECK(h);
       std::swap(cur, nxt);
       if (dbg_layer == i + 1)

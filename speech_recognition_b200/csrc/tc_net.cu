@@ -491,7 +491,9 @@ int launch_tc_gemm(kws_handle* h, GemmParams& p, cudaStream_t st) {
   }
   const int grid = std::min(p.num_tiles, h->num_sms);
   if (grid <= 0) return KWS_OK;
+  KWS_T0(h, MODE == 0 ? KC_CONV1 : KC_BLOCKS, st);
   tc_gemm_kernel<MODE><<<grid, TC_THREADS, lay.total, st>>>(p);
+  KWS_T1(h, st);
   KWS_LAUNCH_CHECK(h);
   return KWS_OK;
 }

@@ -72,6 +72,18 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.kws_launch_count(self.h))
 
+    KERNEL_CLASSES = ("augment", "dft", "mel_dct", "slice_conv1", "dw_pw_blocks", "head", "other")
+
+    def timing_enable(self, on=True):
+        self._check(self.lib.kws_timing_enable(self.h, int(bool(on))))
+
+    def timing_read(self):
+        """{class: (total_ms, launches)} since the last read (synchronises)."""
+        ms = (C.c_double * 7)()
+        cnt = (C.c_int64 * 7)()
+        self._check(self.lib.kws_timing_read(self.h, ms, cnt, 7))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
+
     # -- stage 1a --
     def set_noise_bank(self, bank_t, file_offsets):
         """bank_t: torch CUDA f32 tensor (kept alive here); file_offsets: int64 [n_files+1]."""

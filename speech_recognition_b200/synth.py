@@ -85,7 +85,7 @@ def make_noise_bank(seconds: int = 60, seed: int = SEED + 7):
 
 
 def raw_synthetic_weights(arch: int, seed: int | None = None, head_gain: float | None = None,
-                          attn_gain: float = 8.0):
+                          attn_gain: float = 2.0):
     """Seeded Glorot-uniform kernels with *uncalibrated* BatchNorm statistics."""
     rs = np.random.RandomState(arch if seed is None else seed)
     if head_gain is None:

@@ -33,3 +33,17 @@ for layer in range(0, last + 1):
 eng.set_precision("fp32"); p32, a32 = eng.forward(x, views=TTA_8)
 eng.set_precision("tc"); ptc, atc = eng.forward(x, views=TTA_8)
 print("probs max abs diff", (p32 - ptc).abs().max().item(), "labels", a32.tolist(), atc.tolist())
+
+# label agreement at scale (GPU fp32 tier == oracle to 1e-6, so it stands in for the oracle here)
+eng2 = Engine(device=0, max_rows=2048, precision="fp32")
+eng2.load_model(0, arch, w)
+N = 8192
+xb = torch.from_numpy(synth.make_clips(N, seed=77)).cuda()
+for views, name in ((((0, 1.0),), "1 view"), (TTA_8, "8 views")):
+    eng2.set_precision("fp32"); p32, a32 = eng2.forward(xb, views=views)
+    eng2.set_precision("tc"); ptc, atc = eng2.forward(xb, views=views)
+    e = (p32 - ptc).abs()
+    top2 = p32.topk(2, dim=1).values
+    print(f"{name}: N={N} label agreement {(a32 == atc).float().mean().item():.5f}  prob err max {e.max().item():.4f} "
+          f"q99 {e.flatten().quantile(0.99).item():.5f} mean {e.mean().item():.2e}; disagreeing clips' margin max "
+          f"{((top2[:,0]-top2[:,1])[a32 != atc]).max().item() if (a32 != atc).any() else 0:.4f}")
