@@ -43,7 +43,8 @@ struct Model {
   // tensor-core operand images (fp16, pre-swizzled UMMA K-major SW128 slabs)
   void* tc_blob = nullptr;
   __half* tc_conv1 = nullptr;             // [2 slabs][c0 rows][64] swizzled, 80 folded taps
-  __half* tc_pw[NUM_BLOCKS];              // [cin/64 slabs][cout rows][64] swizzled
+  __half* tc_pw[NUM_BLOCKS];              // [cin/64 slabs][cout rows][64] swizzled, BN scale folded in
+  __half* tc_dw[NUM_BLOCKS];              // depthwise taps [3][cin] fp16
   size_t max_act_elems = 0;               // max over layers of T*C (per clip-view)
 };
 

@@ -12,7 +12,8 @@
 namespace kws {
 
 int model_build_tc(kws_handle* h, Model& m, const std::vector<std::vector<float>>& pw_host,
-                   const std::vector<float>& conv1_host);   // tc_net.cu
+                   const std::vector<float>& conv1_host, const std::vector<std::vector<float>>& dw_host,
+                   const std::vector<std::vector<float>>& scales);   // tc_net.cu
 
 namespace {
 
@@ -107,10 +108,11 @@ int model_build(kws_handle* h, int slot, int arch, const kws_tensor_h* t, int n)
     return KWS_OK;
   };
   if ((rc = fold_bn(0, m.c0))) return rc;
-  std::vector<std::vector<float>> pw_host(NUM_BLOCKS);
+  std::vector<std::vector<float>> pw_host(NUM_BLOCKS), dw_host(NUM_BLOCKS);
   for (int i = 0; i < NUM_BLOCKS; ++i) {
     const LayerDesc& d = m.layers[i];
     if ((rc = get("depthwise_conv2d_" + std::to_string(i + 1) + "/depthwise_kernel", 3LL * d.cin, &p))) return rc;
+    dw_host[i].assign(p, p + 3 * d.cin);
     o_dw[i] = push(p, 3 * d.cin); push_pad();                  // [1,3,C,1] -> [3,C]
     if ((rc = get("conv1d_" + std::to_string(i + 2) + "/kernel", 1LL * d.cin * d.cout, &p))) return rc;
     pw_host[i].assign(p, p + static_cast<size_t>(d.cin) * d.cout);
@@ -135,8 +137,8 @@ int model_build(kws_handle* h, int slot, int arch, const kws_tensor_h* t, int n)
   for (int i = 0; i < NUM_BLOCKS; ++i) { m.w_dw[i] = m.blob + o_dw[i]; m.w_pw[i] = m.blob + o_pw[i]; }
   m.w_d1 = m.blob + o_d1; m.b_d1 = m.blob + o_b1; m.w_d2 = m.blob + o_d2;
 
-  // tensor-core operand images (fp16, pre-swizzled); BN scale/shift stay fp32 in the epilogue
-  if ((rc = model_build_tc(h, m, pw_host, conv1_host))) return rc;
+  // tensor-core operand images (fp16, pre-swizzled, BN scale folded in); the BN shift stays fp32
+  if ((rc = model_build_tc(h, m, pw_host, conv1_host, dw_host, scales))) return rc;
   m.loaded = true;
   return KWS_OK;
 }

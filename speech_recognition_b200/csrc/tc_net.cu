@@ -6,19 +6,27 @@
 //                      layer is a K=80 contraction against taps pre-summed on the host
 //                      (W80[u] = sum_f W[f, u-20f]); the TTA view (np.roll + gain,
 //                      make_submission.py:126-130) is applied while the waveform window is staged.
-//   * K6 dw_pw_block : depthwise k3 FIR (CUDA cores, fp32) as the A-operand producer of the
-//                      pointwise GEMM + BN + ReLU6 epilogue.
-// Roles (448 threads, 1 CTA / SM):
-//   warps 0-3  epilogue : tcgen05.ld accumulator -> acc*scale+shift -> ReLU6 -> fp16 -> global
-//   warp  4    MMA      : one thread issues tcgen05.mma (A,B from swizzled smem, D in TMEM)
-//   warp  5    B loader : cp.async.bulk of pre-swizzled fp16 weight slabs (resident when they fit)
-//   warps 6-13 A producers
-// Pipelines: A ring (producers <-> MMA), B ring (loader <-> MMA), accumulator stages in TMEM
-// (MMA <-> epilogue), all on mbarriers; tcgen05.commit releases smem slots / publishes accumulators.
+//   * K6 dw_pw_block : depthwise k3 FIR (CUDA cores) as the A-operand producer of the pointwise
+//                      GEMM, BN + ReLU6 in the epilogue.
+// Roles (480 threads, 1 CTA / SM, static round-robin over 128-row tiles):
+//   warps 0-3  epilogue   : tcgen05.ld accumulator -> +shift -> ReLU6 -> fp16 -> global
+//   warp  4    MMA        : one thread issues tcgen05.mma (A,B from swizzled smem, D in TMEM)
+//   warp  5    B loader   : cp.async.bulk of pre-swizzled fp16 weight blocks (resident when they fit)
+//   warp  6    raw loader : cp.async.bulk.tensor (TMA) of the previous activation's rows, one
+//                           [rows x 64 channel] box per K slab, several slabs ahead of the producers
+//   warps 7-14 A producers: two groups of 128 threads working on alternate K slabs; each thread
+//                           slides a 3-row window over 8 consecutive output rows of one 8-channel
+//                           chunk (packed half2 FMAs) and stores the UMMA-swizzled A slab
+// Pipelines: raw ring (TMA <-> producers), A ring (producers <-> MMA), B ring (loader <-> MMA),
+// accumulator stages in TMEM (MMA <-> epilogue), all on mbarriers; tcgen05.commit releases smem
+// slots / publishes accumulators.
 // Operands are fp16 (same tensor rate as bf16, 3 more mantissa bits; ReLU6 bounds activations to
-// [0,6] so the range is safe), accumulation is fp32 in TMEM, BN scale/shift stay fp32.
+// [0,6] so the range is safe), accumulation is fp32 in TMEM.  The BatchNorm scale is folded into
+// the fp16 weights at load time, the shift stays fp32 in the epilogue.
 #include <algorithm>
 #include <cstring>
+
+#include <cuda.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -32,11 +40,15 @@ namespace {
 constexpr int NUM_EPI_WARPS = 4;
 constexpr int NUM_PROD_WARPS = 8;
 constexpr int NUM_PROD_THREADS = NUM_PROD_WARPS * 32;           // 256
+constexpr int PROD_GROUPS = 2;                                   // dw_pw: groups on alternate slabs
+constexpr int GROUP_THREADS = NUM_PROD_THREADS / PROD_GROUPS;    // 128
 constexpr int MMA_WARP = NUM_EPI_WARPS;                          // 4
 constexpr int LOAD_WARP = NUM_EPI_WARPS + 1;                     // 5
-constexpr int PROD_WARP0 = NUM_EPI_WARPS + 2;                    // 6
-constexpr int TC_THREADS = 32 * (NUM_EPI_WARPS + 2 + NUM_PROD_WARPS);   // 448
-constexpr int MAX_STAGES = 8;
+constexpr int RAW_WARP = NUM_EPI_WARPS + 2;                      // 6
+constexpr int PROD_WARP0 = NUM_EPI_WARPS + 3;                    // 7
+constexpr int TC_THREADS = 32 * (PROD_WARP0 + NUM_PROD_WARPS);   // 480
+constexpr int MAX_STAGES = 8;                                    // A / raw rings
+constexpr int MAX_B_BLOCKS = 16;                                 // B ring (K slabs x N halves)
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_LIMIT = 227 * 1024;
 
@@ -44,18 +56,21 @@ constexpr int CONV1_K = 80;                                      // samples per 
 constexpr int CONV1_ROW_HOP = 40;
 constexpr int CONV1_WIN = CONV1_ROW_HOP * (TILE_M - 1) + CONV1_K;   // 5160 staged samples per tile
 
-struct GemmParams {
-  // A-side sources
-  const __half* act_in;     // dw_pw: previous activation [rows_in, cin] fp16
-  const float* wav;         // conv1: waveforms [B, 16000] fp32
-  const float* dw;          // dw_pw: depthwise taps [3][cin] fp32
-  ViewTable vt;             // conv1: TTA views
+constexpr int RAW_BOX_S1 = 160;     // rows of the raw box, stride-1 layers (128 + 2 per clip boundary + 2)
+constexpr int RAW_BOX_S2 = 136;     // stride-2 layers: two boxes of 136 rows (2*127 + 3 + slack)
+
+struct alignas(64) GemmParams {
+  CUtensorMap tmap_in;      // dw_pw: previous activation [rows_in, cin] fp16, box [box_rows, 64]
+  // conv1 A side
+  const float* wav;         // waveforms [B, 16000] fp32
+  ViewTable vt;             // TTA views
   int n_views;
-  // B side: pre-swizzled fp16 slabs, slab kb at w_img + kb * cout * 128
+  // dw_pw A side
+  const __half* dw_h;       // depthwise taps [3][cin] fp16
+  // B side: pre-swizzled fp16 blocks of n_inst rows x 128 B, block j = (kb, nh) = (j / n_halves, j % n_halves)
   const uint8_t* w_img;
   // epilogue
-  const float* scale;
-  const float* shift;
+  const float* shift;       // beta - mean * scale (the scale lives in the weights)
   __half* out;              // [rows_out, cout] fp16
   // shapes
   int cin, cout, stride, pad_left, t_in, t_out;
@@ -64,26 +79,30 @@ struct GemmParams {
   int tiles_per_group;      // conv1: tiles per clip-view (4); dw_pw: unused
   int num_kb;               // K slabs
   int last_ksteps;          // K=16 steps in the last slab (4, or 1 for conv1)
-  int a_stages, b_stages, acc_stages, b_resident;
+  int a_stages, b_stages, acc_stages, b_resident, raw_stages;
   int n_inst, n_halves;     // cout = n_inst * n_halves, n_inst <= 256
   int a_stage_bytes;        // dw_pw: 16 KB; conv1: 32 KB (both slabs of a tile)
+  int raw_stage_bytes, box_rows, n_boxes;
 };
 
 struct SmemLayout {
-  uint32_t a_off, b_off, aux_off, bar_off, total;
+  uint32_t a_off, b_off, raw_off, aux_off, bar_off, total;
 };
 
 __host__ __device__ inline SmemLayout smem_layout(const GemmParams& p, bool conv1) {
   SmemLayout s;
   uint32_t o = 0;
   s.a_off = o; o += static_cast<uint32_t>(p.a_stages) * p.a_stage_bytes;
-  s.b_off = o; o += static_cast<uint32_t>(p.b_stages) * p.cout * ROW_BYTES;
+  s.b_off = o; o += static_cast<uint32_t>(p.b_stages) * p.n_inst * ROW_BYTES;
+  s.raw_off = o; o += static_cast<uint32_t>(p.raw_stages) * p.raw_stage_bytes;
   s.aux_off = o;
-  // aux: scale[cout] shift[cout] fp32, then dw taps [3*cin] fp32 (dw_pw) or the staged fp16 window (conv1)
-  o += 2u * p.cout * 4u;
-  o += conv1 ? static_cast<uint32_t>(((CONV1_WIN + 8) * 2 + 15) & ~15) : 3u * p.cin * 4u;
+  // aux: shift[cout] fp32, then (dw_pw) taps [3*cin] fp16 + row metadata [2 groups][2 parities][128] u32
+  //      or (conv1) the staged fp16 waveform window
+  o += static_cast<uint32_t>(p.cout) * 4u;
+  o += conv1 ? static_cast<uint32_t>(((CONV1_WIN + 8) * 2 + 15) & ~15)
+             : (static_cast<uint32_t>(3 * p.cin * 2 + 15) & ~15u) + PROD_GROUPS * 2 * TILE_M * 4u;
   o = (o + 15u) & ~15u;
-  s.bar_off = o; o += (4 * MAX_STAGES + 4) * 8 + 16;
+  s.bar_off = o; o += (4 * MAX_STAGES + 2 * MAX_B_BLOCKS + 4) * 8 + 16;
   s.total = o + 1024;        // slack for the manual 1024-byte alignment of the base
   return s;
 }
@@ -92,113 +111,77 @@ __host__ __device__ inline SmemLayout smem_layout(const GemmParams& p, bool conv
 // A producers
 // ------------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ void unpack8(const uint4& v, float* x) {
-  const __half2* h = reinterpret_cast<const __half2*>(&v);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 f = __half22float2(h[i]);
-    x[2 * i] = f.x; x[2 * i + 1] = f.y;
-  }
-}
-__device__ __forceinline__ uint4 pack8(const float* x) {
-  uint4 v;
-  __half2* h = reinterpret_cast<__half2*>(&v);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
-  return v;
+// Row metadata of a 128-row output tile (dw_pw), one word per output row:
+//   bits  0-15 : row of tap 0 inside the raw box (relative to the box's first row)
+//   bits 16-18 : validity of taps 0..2 (TF 'SAME' zero padding)
+//   bit  19    : the previous output row belongs to the same clip-view (the window can slide)
+__device__ __forceinline__ uint32_t row_meta(const GemmParams& p, int stride, int tile, int r) {
+  const int m0 = tile * TILE_M;
+  const int v0 = m0 / p.t_out, t0 = m0 - v0 * p.t_out;
+  const int lo = v0 * p.t_in + t0 * stride - p.pad_left;      // first row of the raw box
+  int m = m0 + r;
+  const bool valid = m < p.rows_out;
+  if (!valid) m = p.rows_out - 1;                              // finite data; the row is never stored
+  const int v = m / p.t_out, t = m - v * p.t_out;
+  const int ti0 = t * stride - p.pad_left;
+  const int rel = v * p.t_in + ti0 - lo;
+  uint32_t mask = 0;
+  if (ti0 >= 0) mask |= 1u;
+  if (ti0 + 1 < p.t_in) mask |= 2u;
+  if (ti0 + 2 < p.t_in) mask |= 4u;
+  const uint32_t cont = (valid && t > 0) ? 1u : 0u;
+  return static_cast<uint32_t>(rel) | (mask << 16) | (cont << 19);
 }
 
-// Depthwise producer: thread = (16-byte channel chunk c of the 64-channel slab, group g of 4
-// consecutive output rows).  STRIDE is the depthwise stride (1 VALID / 2 SAME).
+__device__ __forceinline__ uint4 lds128(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
+
+__device__ __forceinline__ uint4 fir3(const uint4& x0, const uint4& x1, const uint4& x2, const uint4& k0,
+                                      const uint4& k1, const uint4& k2) {
+  uint4 o;
+  const __half2* a = reinterpret_cast<const __half2*>(&x0);
+  const __half2* b = reinterpret_cast<const __half2*>(&x1);
+  const __half2* c = reinterpret_cast<const __half2*>(&x2);
+  const __half2* ka = reinterpret_cast<const __half2*>(&k0);
+  const __half2* kb = reinterpret_cast<const __half2*>(&k1);
+  const __half2* kc = reinterpret_cast<const __half2*>(&k2);
+  __half2* r = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) r[q] = __hfma2(c[q], kc[q], __hfma2(b[q], kb[q], __hmul2(a[q], ka[q])));
+  return o;
+}
+
+// One K slab (64 channels) of a 128-row tile by one producer group: thread = (16-byte channel
+// chunk c, run of 8 consecutive output rows).  raw = [box rows][64 ch] fp16 (dense 128-byte rows).
 template <int STRIDE>
-struct DwProducer {
-  int c, g;
-  int in_row0[4];            // index into act_in rows of tap 0 for each of the 4 output rows (may be <0)
-  int t0[4];                 // t*stride - pad_left (time index of tap 0 inside the clip)
-  bool valid[4];
-  bool same_clip;
-
-  __device__ __forceinline__ void begin_tile(const GemmParams& p, int tile, int ptid) {
-    c = ptid & 7; g = ptid >> 3;
-    const int m0 = tile * TILE_M + 4 * g;
-    int rv0 = -1;
-    same_clip = true;
+__device__ __forceinline__ void produce_slab(const uint8_t* raw, uint8_t* slab, const uint32_t* meta,
+                                             const __half* s_dwh, int cin, int kb, int tg) {
+  const int c = tg & 7, g = tg >> 3;
+  const int ch0 = kb * SLAB_K + c * 8;
+  const uint4 k0 = *reinterpret_cast<const uint4*>(s_dwh + ch0);
+  const uint4 k1 = *reinterpret_cast<const uint4*>(s_dwh + cin + ch0);
+  const uint4 k2 = *reinterpret_cast<const uint4*>(s_dwh + 2 * cin + ch0);
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  uint4 w0 = zero, w1 = zero, w2 = zero;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int m = m0 + i;
-      valid[i] = m < p.rows_out;
-      const int mm = valid[i] ? m : 0;
-      const int rv = mm / p.t_out, t = mm - rv * p.t_out;
-      t0[i] = t * STRIDE - p.pad_left;
-      in_row0[i] = rv * p.t_in + t0[i];
-      if (i == 0) rv0 = rv;
-      if (rv != rv0 || !valid[i]) same_clip = false;
-    }
-  }
-
-  __device__ __forceinline__ void produce(const GemmParams& p, uint8_t* slab, int kb, const float* s_dw) const {
-    const int ch0 = kb * SLAB_K + c * 8;
-    float w[3][8];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const float4 a = *reinterpret_cast<const float4*>(s_dw + j * p.cin + ch0);
-      const float4 b = *reinterpret_cast<const float4*>(s_dw + j * p.cin + ch0 + 4);
-      w[j][0] = a.x; w[j][1] = a.y; w[j][2] = a.z; w[j][3] = a.w;
-      w[j][4] = b.x; w[j][5] = b.y; w[j][6] = b.z; w[j][7] = b.w;
-    }
-    float acc[4][8];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[i][e] = 0.0f;
-    const __half* base = p.act_in + ch0;
-    if (same_clip) {
-      // sliding window: input rows q = 0 .. 3*STRIDE+2 relative to tap 0 of output row 0
-      constexpr int NQ = 3 * STRIDE + 3;
-      uint4 v[NQ];
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        const int ti = t0[0] + q;
-        v[q] = make_uint4(0u, 0u, 0u, 0u);
-        if (ti >= 0 && ti < p.t_in)
-          v[q] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(in_row0[0] + q) * p.cin));
-      }
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        float x[8];
-        unpack8(v[q], x);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int j = q - i * STRIDE;
-          if (j >= 0 && j < 3) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[i][e] = fmaf(w[j][e], x[e], acc[i][e]);
-          }
-        }
-      }
+  for (int i = 0; i < 8; ++i) {
+    const int r = 8 * g + i;
+    const uint32_t mt = meta[r];
+    const uint8_t* src = raw + (mt & 0xffffu) * ROW_BYTES + c * 16;
+    const bool cont = (i > 0) && ((mt >> 19) & 1u);
+    if (STRIDE == 1) {
+      // VALID convolution: every tap of a valid row is inside its clip
+      if (cont) { w0 = w1; w1 = w2; }
+      else { w0 = lds128(src); w1 = lds128(src + ROW_BYTES); }
+      w2 = lds128(src + 2 * ROW_BYTES);
     } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (!valid[i]) continue;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const int ti = t0[i] + j;
-          if (ti < 0 || ti >= p.t_in) continue;
-          const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(in_row0[i] + j) * p.cin));
-          float x[8];
-          unpack8(v, x);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[i][e] = fmaf(w[j][e], x[e], acc[i][e]);
-        }
-      }
+      if (cont) w0 = w2;
+      else w0 = ((mt >> 16) & 1u) ? lds128(src) : zero;
+      w1 = lds128(src + ROW_BYTES);
+      w2 = ((mt >> 18) & 1u) ? lds128(src + 2 * ROW_BYTES) : zero;
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t r = 4 * g + i;
-      *reinterpret_cast<uint4*>(slab + swz_off(r, c)) = pack8(acc[i]);
-    }
+    *reinterpret_cast<uint4*>(slab + swz_off(r, c)) = fir3(w0, w1, w2, k0, k1, k2);
   }
-};
+}
 
 // conv1 producer: stage the 5160-sample window of (clip-view, row block) in smem as fp16 with the
 // TTA view applied (coalesced scalar loads, circular index), then copy 16-byte chunks into the
@@ -234,43 +217,72 @@ struct Conv1Producer {
 };
 
 // ------------------------------------------------------------------------------------------------
+// epilogue: 32 accumulator columns of one row -> +shift -> ReLU6 -> 32 fp16 (64 bytes)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const float* s_shift32, __half* dst,
+                                               bool ok) {
+  const __half2 six = __float2half2_rn(6.0f);
+  uint32_t o[16];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 sh = *reinterpret_cast<const float4*>(s_shift32 + 4 * q);
+    const uint32_t a = pack_relu_f16x2(__uint_as_float(v[4 * q]) + sh.x, __uint_as_float(v[4 * q + 1]) + sh.y);
+    const uint32_t b = pack_relu_f16x2(__uint_as_float(v[4 * q + 2]) + sh.z, __uint_as_float(v[4 * q + 3]) + sh.w);
+    const __half2 ha = __hmin2(*reinterpret_cast<const __half2*>(&a), six);
+    const __half2 hb = __hmin2(*reinterpret_cast<const __half2*>(&b), six);
+    o[2 * q] = *reinterpret_cast<const uint32_t*>(&ha);
+    o[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&hb);
+  }
+  if (ok) {
+    uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) d[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
 template <int MODE>   // 0 = conv1, 1 = dw_pw stride 1, 2 = dw_pw stride 2
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const GemmParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr bool kConv1 = (MODE == 0);
+  constexpr int kStride = (MODE == 2) ? 2 : 1;
   const SmemLayout lay = smem_layout(p, kConv1);
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_base = smem + lay.a_off;
   uint8_t* b_base = smem + lay.b_off;
-  float* s_scale = reinterpret_cast<float*>(smem + lay.aux_off);
-  float* s_shift = s_scale + p.cout;
-  float* s_dw = s_shift + p.cout;                              // dw_pw
-  __half* s_win = reinterpret_cast<__half*>(s_shift + p.cout); // conv1
+  uint8_t* raw_base = smem + lay.raw_off;
+  float* s_shift = reinterpret_cast<float*>(smem + lay.aux_off);
+  __half* s_dwh = reinterpret_cast<__half*>(s_shift + p.cout);                       // dw_pw
+  uint32_t* s_meta = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(s_dwh) + ((3 * p.cin * 2 + 15) & ~15));
+  __half* s_win = reinterpret_cast<__half*>(s_shift + p.cout);                       // conv1
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_off);
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + MAX_STAGES;
-  uint64_t* b_full = bars + 2 * MAX_STAGES;
-  uint64_t* b_empty = bars + 3 * MAX_STAGES;
-  uint64_t* acc_full = bars + 4 * MAX_STAGES;
-  uint64_t* acc_empty = bars + 4 * MAX_STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * MAX_STAGES + 4);
+  uint64_t* raw_full = bars + 2 * MAX_STAGES;
+  uint64_t* raw_empty = bars + 3 * MAX_STAGES;
+  uint64_t* b_full = bars + 4 * MAX_STAGES;
+  uint64_t* b_empty = b_full + MAX_B_BLOCKS;
+  uint64_t* acc_full = b_empty + MAX_B_BLOCKS;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // ---- one-time setup ----
-  for (int i = tid; i < p.cout; i += TC_THREADS) { s_scale[i] = p.scale[i]; s_shift[i] = p.shift[i]; }
+  for (int i = tid; i < p.cout; i += TC_THREADS) s_shift[i] = p.shift[i];
   if (!kConv1)
-    for (int i = tid; i < 3 * p.cin; i += TC_THREADS) s_dw[i] = p.dw[i];
+    for (int i = tid; i < 3 * p.cin; i += TC_THREADS) s_dwh[i] = p.dw_h[i];
   if (warp == MMA_WARP) {
     if (lane == 0) {
       for (int i = 0; i < MAX_STAGES; ++i) {
-        mbar_init(&a_full[i], NUM_PROD_THREADS);
+        mbar_init(&a_full[i], kConv1 ? NUM_PROD_THREADS : GROUP_THREADS);
         mbar_init(&a_empty[i], 1);
-        mbar_init(&b_full[i], 1);
-        mbar_init(&b_empty[i], 1);
+        mbar_init(&raw_full[i], 1);
+        mbar_init(&raw_empty[i], GROUP_THREADS);
       }
+      for (int i = 0; i < MAX_B_BLOCKS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
       for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NUM_EPI_WARPS * 32); }
       fence_mbar_init();
     }
@@ -278,11 +290,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const GemmParams
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
+  if (!kConv1 && warp == RAW_WARP && lane == 0) tma_prefetch_desc(&p.tmap_in);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t b_slab_bytes = static_cast<uint32_t>(p.cout) * ROW_BYTES;
+  const uint32_t b_block_bytes = static_cast<uint32_t>(p.n_inst) * ROW_BYTES;
+  const int blocks_per_tile = p.num_kb * p.n_halves;
 
   if (warp < NUM_EPI_WARPS) {
     // =========================== epilogue ===========================
@@ -290,8 +304,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const GemmParams
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      // output row of this thread
-      const int r = warp * 32 + lane;
+      const int r = warp * 32 + lane;                            // output row of this thread
       long long orow;
       bool ok;
       if (kConv1) {
@@ -305,19 +318,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const GemmParams
       }
       __half* optr = p.out + orow * p.cout;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(acc * p.cout);
-      for (int c0 = 0; c0 < p.cout; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c0, v);
+      // two register buffers: the TMEM load of the next 32 columns is in flight during the math
+      uint32_t va[32], vb[32];
+      tmem_ld32(taddr, va);
+      for (int c0 = 0; c0 < p.cout; c0 += 64) {
         tmem_ld_wait();
-        float y[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float a = __uint_as_float(v[e]);
-          y[e] = fminf(fmaxf(fmaf(a, s_scale[c0 + e], s_shift[c0 + e]), 0.0f), 6.0f);   // BN + ReLU6
-        }
-        if (ok) {
-          *reinterpret_cast<uint4*>(optr + c0) = pack8(y);
-          *reinterpret_cast<uint4*>(optr + c0 + 8) = pack8(y + 8);
+        if (c0 + 32 < p.cout) tmem_ld32(taddr + c0 + 32, vb);
+        epilogue_chunk(va, s_shift + c0, optr + c0, ok);
+        if (c0 + 32 < p.cout) {
+          tmem_ld_wait();
+          if (c0 + 64 < p.cout) tmem_ld32(taddr + c0 + 64, va);
+          epilogue_chunk(vb, s_shift + c0 + 32, optr + c0 + 32, ok);
         }
       }
       tc_fence_before();
@@ -333,9 +344,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const GemmParams
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d0 = tmem_base + static_cast<uint32_t>(acc * p.cout);
-        if (kConv1) {
-          mbar_wait(&a_full[sa], pa);                          // one stage = both slabs of the tile
-        }
+        if (kConv1) mbar_wait(&a_full[sa], pa);                  // one stage = both slabs of the tile
         for (int kb = 0; kb < p.num_kb; ++kb) {
           uint32_t a_addr;
           if (kConv1) {
@@ -344,30 +353,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const GemmParams
             mbar_wait(&a_full[sa], pa);
             a_addr = smem_u32(a_base + sa * p.a_stage_bytes);
           }
-          uint32_t b_addr;
-          if (p.b_resident) {
-            mbar_wait(&b_full[kb], 0);
-            b_addr = smem_u32(b_base + kb * b_slab_bytes);
-          } else {
-            mbar_wait(&b_full[sb], pb);
-            b_addr = smem_u32(b_base + sb * b_slab_bytes);
-          }
-          tc_fence_after();
           const int ksteps = (kb == p.num_kb - 1) ? p.last_ksteps : 4;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t adesc = umma_desc_sw128(a_addr + ks * 32);
-            for (int nh = 0; nh < p.n_halves; ++nh) {
-              const uint64_t bdesc = umma_desc_sw128(b_addr + nh * p.n_inst * ROW_BYTES + ks * 32);
-              umma_f16(d0 + nh * p.n_inst, adesc, bdesc, idesc, (kb | ks) != 0 ? 1u : 0u);
+          for (int nh = 0; nh < p.n_halves; ++nh) {
+            uint32_t b_addr;
+            if (p.b_resident) {
+              const int j = kb * p.n_halves + nh;
+              mbar_wait(&b_full[j], 0);
+              b_addr = smem_u32(b_base + j * b_block_bytes);
+            } else {
+              mbar_wait(&b_full[sb], pb);
+              b_addr = smem_u32(b_base + sb * b_block_bytes);
+            }
+            tc_fence_after();
+            for (int ks = 0; ks < ksteps; ++ks)
+              umma_f16(d0 + nh * p.n_inst, umma_desc_sw128(a_addr + ks * 32), umma_desc_sw128(b_addr + ks * 32),
+                       idesc, (kb | ks) != 0 ? 1u : 0u);
+            if (!p.b_resident) {
+              umma_commit(&b_empty[sb]);
+              if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
             }
           }
           if (!kConv1) {
             umma_commit(&a_empty[sa]);
             if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
-          }
-          if (!p.b_resident) {
-            umma_commit(&b_empty[sb]);
-            if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
           }
         }
         if (kConv1) {
@@ -381,32 +389,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const GemmParams
   } else if (warp == LOAD_WARP) {
     // =========================== weight loader ===========================
     if (lane == 0) {
+      auto load_block = [&](int j, int slot, uint64_t* bar) {
+        mbar_arrive_expect_tx(bar, b_block_bytes);
+        const uint8_t* src = p.w_img + static_cast<size_t>(j) * b_block_bytes;
+        uint8_t* dst = b_base + slot * b_block_bytes;
+        for (uint32_t o = 0; o < b_block_bytes; o += 16384)
+          bulk_g2s(dst + o, src + o, min(16384u, b_block_bytes - o), bar);
+      };
       if (p.b_resident) {
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_arrive_expect_tx(&b_full[kb], b_slab_bytes);
-          for (uint32_t o = 0; o < b_slab_bytes; o += 16384)
-            bulk_g2s(b_base + kb * b_slab_bytes + o, p.w_img + static_cast<size_t>(kb) * b_slab_bytes + o,
-                     min(16384u, b_slab_bytes - o), &b_full[kb]);
-        }
+        for (int j = 0; j < blocks_per_tile; ++j) load_block(j, j, &b_full[j]);
       } else {
         int sb = 0; uint32_t pb = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-          for (int kb = 0; kb < p.num_kb; ++kb) {
+          for (int j = 0; j < blocks_per_tile; ++j) {
             mbar_wait(&b_empty[sb], pb ^ 1);
-            mbar_arrive_expect_tx(&b_full[sb], b_slab_bytes);
-            for (uint32_t o = 0; o < b_slab_bytes; o += 16384)
-              bulk_g2s(b_base + sb * b_slab_bytes + o, p.w_img + static_cast<size_t>(kb) * b_slab_bytes + o,
-                       min(16384u, b_slab_bytes - o), &b_full[sb]);
+            load_block(j, sb, &b_full[sb]);
             if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
           }
+        }
+      }
+    }
+  } else if (warp == RAW_WARP) {
+    // =========================== raw activation loader (TMA) ===========================
+    if (!kConv1 && lane == 0) {
+      int rs = 0; uint32_t pr = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m0 = tile * TILE_M;
+        const int v0 = m0 / p.t_out, t0 = m0 - v0 * p.t_out;
+        const int lo = v0 * p.t_in + t0 * kStride - p.pad_left;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&raw_empty[rs], pr ^ 1);
+          mbar_arrive_expect_tx(&raw_full[rs], static_cast<uint32_t>(p.raw_stage_bytes));
+          uint8_t* dst = raw_base + rs * p.raw_stage_bytes;
+          for (int bx = 0; bx < p.n_boxes; ++bx)
+            tma_load_2d(dst + bx * p.box_rows * ROW_BYTES, &p.tmap_in, kb * SLAB_K, lo + bx * p.box_rows,
+                        &raw_full[rs]);
+          if (++rs == p.raw_stages) { rs = 0; pr ^= 1; }
         }
       }
     }
   } else {
     // =========================== A producers ===========================
     const int ptid = tid - PROD_WARP0 * 32;
-    int sa = 0; uint32_t pa = 0;
     if constexpr (kConv1) {
+      int sa = 0; uint32_t pa = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         Conv1Producer::stage_window(p, tile, ptid, s_win);
         asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");     // window complete
@@ -418,16 +444,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const GemmParams
         asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");     // window free again
       }
     } else {
-      DwProducer<MODE == 2 ? 2 : 1> prod;
+      const int grp = ptid / GROUP_THREADS, tg = ptid - grp * GROUP_THREADS;
+      uint32_t* meta_g = s_meta + grp * 2 * TILE_M;
+      int n_base = 0, par = 0;                                   // n = running slab number of this CTA
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        prod.begin_tile(p, tile, ptid);
+        uint32_t* meta = meta_g + par * TILE_M;
+        meta[tg] = row_meta(p, kStride, tile, tg);
+        if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(GROUP_THREADS) : "memory");
+        else asm volatile("bar.sync 2, %0;" ::"n"(GROUP_THREADS) : "memory");
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&a_empty[sa], pa ^ 1);
-          prod.produce(p, a_base + sa * p.a_stage_bytes, kb, s_dw);
+          const int n = n_base + kb;
+          if ((n & 1) != grp) continue;
+          const int rs = n % p.raw_stages, sa = n % p.a_stages;
+          mbar_wait(&raw_full[rs], static_cast<uint32_t>(n / p.raw_stages) & 1u);
+          mbar_wait(&a_empty[sa], (static_cast<uint32_t>(n / p.a_stages) & 1u) ^ 1u);
+          produce_slab<kStride>(raw_base + rs * p.raw_stage_bytes, a_base + sa * p.a_stage_bytes, meta, s_dwh,
+                                p.cin, kb, tg);
           fence_proxy_async_smem();
           mbar_arrive(&a_full[sa]);
-          if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+          mbar_arrive(&raw_empty[rs]);
         }
+        n_base += p.num_kb;
+        par ^= 1;
       }
     }
   }
@@ -445,18 +483,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const GemmParams
 // host side
 // ------------------------------------------------------------------------------------------------
 
-// Keras kernel [K, N] (row-major, K = input channel / tap) -> pre-swizzled fp16 slabs
-// [num_kb][N rows x 128 B]; element (k, n) lands in slab k/64, row n, chunk (k%64)/8.
-void build_weight_image(const float* w, int K, int N, std::vector<__half>& img) {
+// Keras kernel [K, N] (row-major, K = input channel / tap), column n scaled by col_scale[n]
+// (the folded BatchNorm scale) -> pre-swizzled fp16 slabs [num_kb][N rows x 128 B]; element
+// (k, n) lands in slab k/64, row n, chunk (k%64)/8.
+void build_weight_image(const float* w, const float* col_scale, int K, int N, std::vector<__half>& img) {
   const int num_kb = (K + SLAB_K - 1) / SLAB_K;
   img.assign(static_cast<size_t>(num_kb) * N * SLAB_K, __float2half_rn(0.0f));
   for (int k = 0; k < K; ++k) {
     const int kb = k / SLAB_K, kk = k % SLAB_K;
     for (int n = 0; n < N; ++n) {
       const size_t byte = static_cast<size_t>(kb) * N * ROW_BYTES + swz_off(n, kk / 8) + (kk % 8) * 2;
-      img[byte / 2] = __float2half_rn(w[static_cast<size_t>(k) * N + n]);
+      img[byte / 2] = __float2half_rn(w[static_cast<size_t>(k) * N + n] * col_scale[n]);
     }
   }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// [rows, cin] fp16 row-major activation, box = [box_rows, 64 channels], dense 128-byte rows in smem
+int make_act_tensor_map(kws_handle* h, CUtensorMap* tm, const __half* act, long long rows, int cin, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(h, KWS_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cin), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cin) * sizeof(__half)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(SLAB_K), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(act), gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, KWS_ECUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(r));
+  return KWS_OK;
 }
 
 template <int MODE>
@@ -465,25 +535,43 @@ int launch_tc_gemm(kws_handle* h, GemmParams& p, cudaStream_t st) {
   // split cout into <= 256-wide instructions
   p.n_halves = p.cout > 256 ? 2 : 1;
   p.n_inst = p.cout / p.n_halves;
-  if (p.n_inst % 16 || p.n_inst > 256 || p.cout > TMEM_COLS)
+  if (p.n_inst % 16 || p.n_inst > 256 || p.cout > TMEM_COLS || p.cout % 32)
     return fail(h, KWS_EUNSUPPORTED, "unsupported channel count for the tensor-core path");
   p.acc_stages = std::min(2, TMEM_COLS / p.cout);
   p.a_stage_bytes = conv1 ? 2 * A_SLAB_BYTES : A_SLAB_BYTES;
-  p.a_stages = conv1 ? 3 : 4;
-  const int b_slab = p.cout * ROW_BYTES;
-  // weights resident in smem when they fit next to the A ring, else a streaming ring
-  p.b_stages = p.num_kb; p.b_resident = 1;
-  SmemLayout lay = smem_layout(p, conv1);
-  if (static_cast<int>(lay.total) > SMEM_LIMIT) {
-    p.b_resident = 0;
-    int budget = SMEM_LIMIT - static_cast<int>(lay.total) + p.b_stages * b_slab;
-    p.b_stages = std::max(1, std::min(MAX_STAGES, budget / b_slab));
-    p.b_stages = std::min(p.b_stages, 4);
-    lay = smem_layout(p, conv1);
-    if (static_cast<int>(lay.total) > SMEM_LIMIT || p.b_stages < 2)
-      return fail(h, KWS_EUNSUPPORTED, "weight slab does not fit in shared memory");
+  const int blocks = p.num_kb * p.n_halves;
+  const int raw_min = conv1 ? 0 : (MODE == 1 ? 3 : 2);
+  const int raw_max = conv1 ? 0 : 6;
+  auto fits = [&](int a, int b, int r) {
+    p.a_stages = a; p.b_stages = b; p.raw_stages = r;
+    return static_cast<int>(smem_layout(p, conv1).total) <= SMEM_LIMIT;
+  };
+  auto best_raw = [&](int a, int b) {          // deepest raw ring that fits, -1 if below the minimum
+    for (int r = raw_max; r >= raw_min; --r)
+      if (fits(a, b, r)) return r;
+    return -1;
+  };
+  bool chosen = false;
+  const int a_try[3] = {conv1 ? 3 : 4, 3, 2};
+  // weights resident in smem when they fit next to the rings, else a streaming ring of blocks
+  if (blocks <= MAX_B_BLOCKS) {
+    for (int ai = 0; ai < 2 && !chosen; ++ai) {
+      const int r = best_raw(a_try[ai], blocks);
+      if (r >= 0) { fits(a_try[ai], blocks, r); p.b_resident = 1; chosen = true; }
+    }
   }
-  if (p.num_kb > MAX_STAGES && p.b_resident) return fail(h, KWS_EUNSUPPORTED, "too many K slabs");
+  if (!chosen) {
+    p.b_resident = 0;
+    const int b_block = p.n_inst * ROW_BYTES;
+    const int b_try[3] = {std::max(2, std::min(4, 65536 / b_block)), 3, 2};
+    for (int bi = 0; bi < 3 && !chosen; ++bi)
+      for (int ai = 0; ai < 3 && !chosen; ++ai) {
+        const int r = best_raw(a_try[ai], b_try[bi]);
+        if (r >= 0) { fits(a_try[ai], b_try[bi], r); chosen = true; }
+      }
+  }
+  if (!chosen) return fail(h, KWS_EUNSUPPORTED, "layer does not fit in shared memory");
+  const SmemLayout lay = smem_layout(p, conv1);
   static bool attr_set[3] = {false, false, false};
   if (!attr_set[MODE]) {
     KWS_CUDA(h, cudaFuncSetAttribute(tc_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -501,7 +589,8 @@ int launch_tc_gemm(kws_handle* h, GemmParams& p, cudaStream_t st) {
 }  // namespace
 
 int model_build_tc(kws_handle* h, Model& m, const std::vector<std::vector<float>>& pw_host,
-                   const std::vector<float>& conv1_host) {
+                   const std::vector<float>& conv1_host, const std::vector<std::vector<float>>& dw_host,
+                   const std::vector<std::vector<float>>& scales) {
   // conv1: fold the 3 overlapping patches into 80 taps: W80[u, co] = sum_f W[f, u - 20 f, co]
   std::vector<float> w80(static_cast<size_t>(CONV1_K) * m.c0, 0.0f);
   for (int f = 0; f < 3; ++f)
@@ -509,19 +598,25 @@ int model_build_tc(kws_handle* h, Model& m, const std::vector<std::vector<float>
       for (int co = 0; co < m.c0; ++co)
         w80[static_cast<size_t>(20 * f + i) * m.c0 + co] += conv1_host[static_cast<size_t>(f * 40 + i) * m.c0 + co];
   std::vector<__half> all, img;
-  std::vector<size_t> offs;
-  build_weight_image(w80.data(), CONV1_K, m.c0, img);
+  std::vector<size_t> offs, dw_offs;
+  auto align_1k = [&]() { while (all.size() % 512) all.push_back(__float2half_rn(0.0f)); };   // 1024-byte aligned
+  build_weight_image(w80.data(), scales[0].data(), CONV1_K, m.c0, img);
   offs.push_back(all.size()); all.insert(all.end(), img.begin(), img.end());
   for (int i = 0; i < NUM_BLOCKS; ++i) {
-    build_weight_image(pw_host[i].data(), m.layers[i].cin, m.layers[i].cout, img);
-    while (all.size() % 512) all.push_back(__float2half_rn(0.0f));      // 1024-byte aligned slabs
+    build_weight_image(pw_host[i].data(), scales[i + 1].data(), m.layers[i].cin, m.layers[i].cout, img);
+    align_1k();
     offs.push_back(all.size()); all.insert(all.end(), img.begin(), img.end());
+  }
+  for (int i = 0; i < NUM_BLOCKS; ++i) {                       // depthwise taps [3][cin] as fp16
+    align_1k();
+    dw_offs.push_back(all.size());
+    for (float v : dw_host[i]) all.push_back(__float2half_rn(v));
   }
   KWS_CUDA(h, cudaMalloc(&m.tc_blob, all.size() * sizeof(__half)));
   KWS_CUDA(h, cudaMemcpy(m.tc_blob, all.data(), all.size() * sizeof(__half), cudaMemcpyHostToDevice));
   __half* base = static_cast<__half*>(m.tc_blob);
   m.tc_conv1 = base + offs[0];
-  for (int i = 0; i < NUM_BLOCKS; ++i) m.tc_pw[i] = base + offs[i + 1];
+  for (int i = 0; i < NUM_BLOCKS; ++i) { m.tc_pw[i] = base + offs[i + 1]; m.tc_dw[i] = base + dw_offs[i]; }
   return KWS_OK;
 }
 
@@ -547,7 +642,7 @@ int launch_forward_tc(kws_handle* h, Model& m, const float* wav, int B, const Vi
       GemmParams p{};
       p.wav = wav + static_cast<size_t>(b0) * L; p.vt = vt; p.n_views = V;
       p.w_img = reinterpret_cast<const uint8_t*>(m.tc_conv1);
-      p.scale = m.bn_scale[0]; p.shift = m.bn_shift[0]; p.out = cur;
+      p.shift = m.bn_shift[0]; p.out = cur;
       p.cin = CONV1_K; p.cout = m.c0; p.t_out = m.t0; p.rows_out = rows * m.t0;
       p.tiles_per_group = (m.t0 + TILE_M - 1) / TILE_M;
       p.num_tiles = rows * p.tiles_per_group;
@@ -558,16 +653,26 @@ int launch_forward_tc(kws_handle* h, Model& m, const float* wav, int B, const Vi
     if (dbg_layer == 0) return launch_to_float(h, cur, true, dbg_out, static_cast<size_t>(rows) * m.t0 * m.c0, st);
     for (int i = 0; i < NUM_BLOCKS; ++i) {
       const LayerDesc& d = m.layers[i];
+      if (d.cin % SLAB_K) return fail(h, KWS_EUNSUPPORTED, "channel count must be a multiple of 64");
       GemmParams p{};
-      p.act_in = cur; p.dw = m.w_dw[i];
+      p.dw_h = m.tc_dw[i];
       p.w_img = reinterpret_cast<const uint8_t*>(m.tc_pw[i]);
-      p.scale = m.bn_scale[i + 1]; p.shift = m.bn_shift[i + 1]; p.out = nxt;
+      p.shift = m.bn_shift[i + 1]; p.out = nxt;
       p.cin = d.cin; p.cout = d.cout; p.stride = d.stride; p.pad_left = d.pad_left;
       p.t_in = d.t_in; p.t_out = d.t_out; p.rows_out = rows * d.t_out;
       p.num_tiles = (p.rows_out + TILE_M - 1) / TILE_M;
       p.num_kb = d.cin / SLAB_K; p.last_ksteps = 4;
-      if (d.cin % SLAB_K) return fail(h, KWS_EUNSUPPORTED, "channel count must be a multiple of 64");
-      int rc = d.stride == 1 ? launch_tc_gemm<1>(h, p, st) : launch_tc_gemm<2>(h, p, st);
+      p.box_rows = d.stride == 1 ? RAW_BOX_S1 : RAW_BOX_S2;
+      p.n_boxes = d.stride == 1 ? 1 : 2;
+      p.raw_stage_bytes = p.box_rows * p.n_boxes * ROW_BYTES;
+      // worst-case extent of a tile inside the raw box: 127 rows * stride + one jump per clip boundary + 3 taps
+      const int boundaries = (TILE_M + d.t_out - 2) / d.t_out;
+      const int jump = d.stride == 1 ? 2 : 0;   // stride 2: a boundary advances by t_in - 2 t_out + 2 <= 2 rows
+      if ((TILE_M - 1) * d.stride + boundaries * jump + 3 > p.box_rows * p.n_boxes)
+        return fail(h, KWS_EUNSUPPORTED, "tile does not fit the raw activation box");
+      int rc = make_act_tensor_map(h, &p.tmap_in, cur, static_cast<long long>(rows) * d.t_in, d.cin, p.box_rows);
+      if (rc) return rc;
+      rc = d.stride == 1 ? launch_tc_gemm<1>(h, p, st) : launch_tc_gemm<2>(h, p, st);
       if (rc) return rc;
       std::swap(cur, nxt);
       if (dbg_layer == i + 1)
