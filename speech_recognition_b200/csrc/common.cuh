@@ -58,10 +58,13 @@ struct Frontend {
   // sparse mel (each bin feeds <= 2 filters)
   int*   mel_idx = nullptr;               // [n_bins][2]
   float* mel_val = nullptr;               // [n_bins][2]
-  void*  tc_blob = nullptr;               // split-fp16 DFT basis images for the tcgen05 path
-  __half* tc_basis_hi = nullptr;
-  __half* tc_basis_lo = nullptr;
-  int tc_kblocks = 0, tc_ncols = 0;
+  // tensor-core tier (tc_frontend.cu): split-fp16 basis blocks, banded-mel table, padded DCT
+  void*  tc_blob = nullptr;
+  bool   tc_ok = false;                   // this configuration is served by the tcgen05 kernel
+  const uint8_t* tc_basis = nullptr;
+  const float* tc_bin_tab = nullptr;
+  const float* tc_dct = nullptr;
+  int tc_kblocks = 0, tc_last_ksteps = 0;
 };
 
 }  // namespace kws
