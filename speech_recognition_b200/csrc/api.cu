@@ -2,6 +2,7 @@
 // host-buffer entry points (pinned-agnostic H2D/D2H pipeline on two streams) and
 // dispatch to the kernel launchers.  No CPU fallback exists anywhere below.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -10,6 +11,11 @@
 namespace kws {
 
 static thread_local std::string g_create_error;
+
+bool debug_sync() {
+  static const bool on = [] { const char* e = getenv("KWS_DEBUG_SYNC"); return e && e[0] == '1'; }();
+  return on;
+}
 
 int fail(kws_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg; else g_create_error = msg;

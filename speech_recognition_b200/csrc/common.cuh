@@ -104,6 +104,7 @@ struct kws_handle {
 namespace kws {
 
 int fail(kws_handle* h, int code, const std::string& msg);
+bool debug_sync();   // KWS_DEBUG_SYNC=1: synchronise after every launch so a fault names its kernel
 int ensure_bytes(kws_handle* h, void** p, size_t* cur, size_t need, bool pinned = false);
 
 #define KWS_CUDA(h, expr)                                                              \
@@ -117,6 +118,7 @@ int ensure_bytes(kws_handle* h, void** p, size_t* cur, size_t need, bool pinned 
   do {                                                                                 \
     (h)->launches++;                                                                   \
     cudaError_t _e = cudaGetLastError();                                               \
+    if (_e == cudaSuccess && kws::debug_sync()) _e = cudaDeviceSynchronize();          \
     if (_e != cudaSuccess)                                                             \
       return kws::fail((h), KWS_ECUDA, std::string("kernel launch at ") + __FILE__ + ":" + \
                                            std::to_string(__LINE__) + ": " + cudaGetErrorString(_e)); \

@@ -79,6 +79,24 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, in
       "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
+// TMA tiled tensor stores shared -> global (bulk async-group completion); elements outside the
+// tensor are clipped.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, int c0, int c1, const void* smem_src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(c0),
+               "r"(c1), "r"(smem_u32(smem_src))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* tmap, int c0, int c1, int c2, const void* smem_src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tmap), "r"(c0),
+               "r"(c1), "r"(c2), "r"(smem_u32(smem_src))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {      // <= N groups still reading their smem source
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_group_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

@@ -56,11 +56,11 @@ constexpr int CONV1_K = 80;                                      // samples per 
 constexpr int CONV1_ROW_HOP = 40;
 constexpr int CONV1_WIN = CONV1_ROW_HOP * (TILE_M - 1) + CONV1_K;   // 5160 staged samples per tile
 
-constexpr int RAW_BOX_S1 = 160;     // rows of the raw box, stride-1 layers (128 + 2 per clip boundary + 2)
-constexpr int RAW_BOX_S2 = 136;     // stride-2 layers: two boxes of 136 rows (2*127 + 3 + slack)
 
 struct alignas(64) GemmParams {
   CUtensorMap tmap_in;      // dw_pw: previous activation [rows_in, cin] fp16, box [box_rows, 64]
+  CUtensorMap tmap_out;     // output activation, box [32 rows, 64 ch], 128-byte swizzle; dw_pw: 2-D
+                            // [rows_out, cout]; conv1: 3-D [clip-views, t_out, cout] (rows clipped per view)
   // conv1 A side
   const float* wav;         // waveforms [B, 16000] fp32
   ViewTable vt;             // TTA views
@@ -71,7 +71,6 @@ struct alignas(64) GemmParams {
   const uint8_t* w_img;
   // epilogue
   const float* shift;       // beta - mean * scale (the scale lives in the weights)
-  __half* out;              // [rows_out, cout] fp16
   // shapes
   int cin, cout, stride, pad_left, t_in, t_out;
   int rows_out;             // valid output rows
@@ -83,10 +82,14 @@ struct alignas(64) GemmParams {
   int n_inst, n_halves;     // cout = n_inst * n_halves, n_inst <= 256
   int a_stage_bytes;        // dw_pw: 16 KB; conv1: 32 KB (both slabs of a tile)
   int raw_stage_bytes, box_rows, n_boxes;
+  unsigned long long t_out_magic;   // ceil(2^40 / t_out)
 };
 
+constexpr int OUT_STAGE_BYTES = 32 * ROW_BYTES;                 // one warp's [32 rows x 64 ch] store box
+constexpr int OUT_BYTES = NUM_EPI_WARPS * 2 * OUT_STAGE_BYTES;  // double-buffered per epilogue warp (32 KB)
+
 struct SmemLayout {
-  uint32_t a_off, b_off, raw_off, aux_off, bar_off, total;
+  uint32_t a_off, b_off, out_off, raw_off, aux_off, bar_off, total;
 };
 
 __host__ __device__ inline SmemLayout smem_layout(const GemmParams& p, bool conv1) {
@@ -94,6 +97,7 @@ __host__ __device__ inline SmemLayout smem_layout(const GemmParams& p, bool conv
   uint32_t o = 0;
   s.a_off = o; o += static_cast<uint32_t>(p.a_stages) * p.a_stage_bytes;
   s.b_off = o; o += static_cast<uint32_t>(p.b_stages) * p.n_inst * ROW_BYTES;
+  s.out_off = o; o += OUT_BYTES;
   s.raw_off = o; o += static_cast<uint32_t>(p.raw_stages) * p.raw_stage_bytes;
   s.aux_off = o;
   // aux: shift[cout] fp32, then (dw_pw) taps [3*cin] fp16 + row metadata [2 groups][2 parities][128] u32
@@ -115,14 +119,17 @@ __host__ __device__ inline SmemLayout smem_layout(const GemmParams& p, bool conv
 //   bits  0-15 : row of tap 0 inside the raw box (relative to the box's first row)
 //   bits 16-18 : validity of taps 0..2 (TF 'SAME' zero padding)
 //   bit  19    : the previous output row belongs to the same clip-view (the window can slide)
+__device__ __forceinline__ int div_t_out(const GemmParams& p, int m) {   // m / t_out, exact for m * t_out < 2^40
+  return static_cast<int>((static_cast<unsigned long long>(m) * p.t_out_magic) >> 40);
+}
 __device__ __forceinline__ uint32_t row_meta(const GemmParams& p, int stride, int tile, int r) {
   const int m0 = tile * TILE_M;
-  const int v0 = m0 / p.t_out, t0 = m0 - v0 * p.t_out;
+  const int v0 = div_t_out(p, m0), t0 = m0 - v0 * p.t_out;
   const int lo = v0 * p.t_in + t0 * stride - p.pad_left;      // first row of the raw box
   int m = m0 + r;
   const bool valid = m < p.rows_out;
   if (!valid) m = p.rows_out - 1;                              // finite data; the row is never stored
-  const int v = m / p.t_out, t = m - v * p.t_out;
+  const int v = div_t_out(p, m), t = m - v * p.t_out;
   const int ti0 = t * stride - p.pad_left;
   const int rel = v * p.t_in + ti0 - lo;
   uint32_t mask = 0;
@@ -152,6 +159,8 @@ __device__ __forceinline__ uint4 fir3(const uint4& x0, const uint4& x1, const ui
 
 // One K slab (64 channels) of a 128-row tile by one producer group: thread = (16-byte channel
 // chunk c, run of 8 consecutive output rows).  raw = [box rows][64 ch] fp16 (dense 128-byte rows).
+// Fast path (the 8 rows continue one clip-view, i.e. almost always when T >= 47): every raw row of
+// the run is loaded up front (10 / 2x9 independent LDS.128), then the FIRs run from registers.
 template <int STRIDE>
 __device__ __forceinline__ void produce_slab(const uint8_t* raw, uint8_t* slab, const uint32_t* meta,
                                              const __half* s_dwh, int cin, int kb, int tg) {
@@ -161,13 +170,43 @@ __device__ __forceinline__ void produce_slab(const uint8_t* raw, uint8_t* slab, 
   const uint4 k1 = *reinterpret_cast<const uint4*>(s_dwh + cin + ch0);
   const uint4 k2 = *reinterpret_cast<const uint4*>(s_dwh + 2 * cin + ch0);
   const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  const uint4 ma = *reinterpret_cast<const uint4*>(meta + 8 * g);
+  const uint4 mb = *reinterpret_cast<const uint4*>(meta + 8 * g + 4);
+  const uint32_t mt[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+  const uint32_t all_cont = mt[1] & mt[2] & mt[3] & mt[4] & mt[5] & mt[6] & mt[7] & (1u << 19);
+  const uint8_t* base = raw + (mt[0] & 0xffffu) * ROW_BYTES + c * 16;
+  uint8_t* dst = slab + (8 * g) * ROW_BYTES;                     // rows 8g..8g+7 = one swizzle group
+  if (all_cont) {
+    if (STRIDE == 1) {
+      uint4 x[10];
+#pragma unroll
+      for (int i = 0; i < 10; ++i) x[i] = lds128(base + i * ROW_BYTES);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<uint4*>(dst + i * ROW_BYTES + ((c ^ i) << 4)) = fir3(x[i], x[i + 1], x[i + 2], k0, k1, k2);
+    } else {
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        uint4 x[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) x[i] = lds128(base + (8 * hlf + i) * ROW_BYTES);
+        if (hlf == 0 && !((mt[0] >> 16) & 1u)) x[0] = zero;       // left 'SAME' pad: only a run's first row can be t = 0
+        if (hlf == 1 && !((mt[7] >> 18) & 1u)) x[8] = zero;       // right pad: only its last row can be t = T_out - 1
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = 4 * hlf + i;
+          *reinterpret_cast<uint4*>(dst + r * ROW_BYTES + ((c ^ r) << 4)) =
+              fir3(x[2 * i], x[2 * i + 1], x[2 * i + 2], k0, k1, k2);
+        }
+      }
+    }
+    return;
+  }
   uint4 w0 = zero, w1 = zero, w2 = zero;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int r = 8 * g + i;
-    const uint32_t mt = meta[r];
-    const uint8_t* src = raw + (mt & 0xffffu) * ROW_BYTES + c * 16;
-    const bool cont = (i > 0) && ((mt >> 19) & 1u);
+    const uint8_t* src = raw + (mt[i] & 0xffffu) * ROW_BYTES + c * 16;
+    const bool cont = (i > 0) && ((mt[i] >> 19) & 1u);
     if (STRIDE == 1) {
       // VALID convolution: every tap of a valid row is inside its clip
       if (cont) { w0 = w1; w1 = w2; }
@@ -175,11 +214,11 @@ __device__ __forceinline__ void produce_slab(const uint8_t* raw, uint8_t* slab, 
       w2 = lds128(src + 2 * ROW_BYTES);
     } else {
       if (cont) w0 = w2;
-      else w0 = ((mt >> 16) & 1u) ? lds128(src) : zero;
+      else w0 = ((mt[i] >> 16) & 1u) ? lds128(src) : zero;
       w1 = lds128(src + ROW_BYTES);
-      w2 = ((mt >> 18) & 1u) ? lds128(src + 2 * ROW_BYTES) : zero;
+      w2 = ((mt[i] >> 18) & 1u) ? lds128(src + 2 * ROW_BYTES) : zero;
     }
-    *reinterpret_cast<uint4*>(slab + swz_off(r, c)) = fir3(w0, w1, w2, k0, k1, k2);
+    *reinterpret_cast<uint4*>(dst + i * ROW_BYTES + ((c ^ i) << 4)) = fir3(w0, w1, w2, k0, k1, k2);
   }
 }
 
@@ -217,26 +256,26 @@ struct Conv1Producer {
 };
 
 // ------------------------------------------------------------------------------------------------
-// epilogue: 32 accumulator columns of one row -> +shift -> ReLU6 -> 32 fp16 (64 bytes)
+// epilogue: 32 accumulator columns of one row -> +shift -> ReLU6 -> 32 fp16 = chunks ch0..ch0+3 of the
+// row's 128-byte line in the swizzled store box
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const float* s_shift32, __half* dst,
-                                               bool ok) {
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const float* s_shift32, uint8_t* row_base,
+                                               int ch0, int sw) {
   const __half2 six = __float2half2_rn(6.0f);
-  uint32_t o[16];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 sh = *reinterpret_cast<const float4*>(s_shift32 + 4 * q);
-    const uint32_t a = pack_relu_f16x2(__uint_as_float(v[4 * q]) + sh.x, __uint_as_float(v[4 * q + 1]) + sh.y);
-    const uint32_t b = pack_relu_f16x2(__uint_as_float(v[4 * q + 2]) + sh.z, __uint_as_float(v[4 * q + 3]) + sh.w);
-    const __half2 ha = __hmin2(*reinterpret_cast<const __half2*>(&a), six);
-    const __half2 hb = __hmin2(*reinterpret_cast<const __half2*>(&b), six);
-    o[2 * q] = *reinterpret_cast<const uint32_t*>(&ha);
-    o[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&hb);
-  }
-  if (ok) {
-    uint4* d = reinterpret_cast<uint4*>(dst);
+  for (int q = 0; q < 4; ++q) {
+    uint32_t o[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) d[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    for (int e = 0; e < 2; ++e) {
+      const float4 sh = *reinterpret_cast<const float4*>(s_shift32 + 8 * q + 4 * e);
+      const uint32_t a = pack_relu_f16x2(__uint_as_float(v[8 * q + 4 * e]) + sh.x, __uint_as_float(v[8 * q + 4 * e + 1]) + sh.y);
+      const uint32_t b = pack_relu_f16x2(__uint_as_float(v[8 * q + 4 * e + 2]) + sh.z, __uint_as_float(v[8 * q + 4 * e + 3]) + sh.w);
+      const __half2 ha = __hmin2(*reinterpret_cast<const __half2*>(&a), six);
+      const __half2 hb = __hmin2(*reinterpret_cast<const __half2*>(&b), six);
+      o[2 * e] = *reinterpret_cast<const uint32_t*>(&ha);
+      o[2 * e + 1] = *reinterpret_cast<const uint32_t*>(&hb);
+    }
+    *reinterpret_cast<uint4*>(row_base + (((ch0 + q) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -253,6 +292,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   uint8_t* a_base = smem + lay.a_off;
   uint8_t* b_base = smem + lay.b_off;
   uint8_t* raw_base = smem + lay.raw_off;
+  uint8_t* out_base = smem + lay.out_off;
   float* s_shift = reinterpret_cast<float*>(smem + lay.aux_off);
   __half* s_dwh = reinterpret_cast<__half*>(s_shift + p.cout);                       // dw_pw
   uint32_t* s_meta = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(s_dwh) + ((3 * p.cin * 2 + 15) & ~15));
@@ -300,41 +340,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 
   if (warp < NUM_EPI_WARPS) {
     // =========================== epilogue ===========================
+    // Each warp owns 32 accumulator rows.  Per 64 output channels it converts its rows into a
+    // private, 128-byte-swizzled [32 x 64] fp16 box in shared memory (conflict-free 16-byte stores)
+    // and one lane hands the box to the TMA store engine: full 128-byte lines leave the SM, rows
+    // beyond the tensor (or beyond the clip-view for conv1) are clipped by the tensor map.
     int acc = 0; uint32_t acc_phase = 0;
+    uint8_t* my_out = out_base + warp * 2 * OUT_STAGE_BYTES;
+    int obuf = 0;
+    if (lane == 0) tma_prefetch_desc(&p.tmap_out);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      const int r = warp * 32 + lane;                            // output row of this thread
-      long long orow;
-      bool ok;
+      int row0, rv = 0;                                          // first output row of this warp's box
       if (kConv1) {
-        const int rv = tile / p.tiles_per_group, jb = tile - rv * p.tiles_per_group;
-        const int j = jb * TILE_M + r;
-        ok = j < p.t_out;
-        orow = static_cast<long long>(rv) * p.t_out + j;
+        rv = tile / p.tiles_per_group;
+        row0 = (tile - rv * p.tiles_per_group) * TILE_M + warp * 32;
       } else {
-        orow = static_cast<long long>(tile) * TILE_M + r;
-        ok = orow < p.rows_out;
+        row0 = tile * TILE_M + warp * 32;
       }
-      __half* optr = p.out + orow * p.cout;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(acc * p.cout);
-      // two register buffers: the TMEM load of the next 32 columns is in flight during the math
       uint32_t va[32], vb[32];
       tmem_ld32(taddr, va);
       for (int c0 = 0; c0 < p.cout; c0 += 64) {
+        uint8_t* box = my_out + obuf * OUT_STAGE_BYTES;
+        uint8_t* row_base = box + lane * ROW_BYTES;
+        if (lane == 0) bulk_wait_group_read<1>();                // the store that last used this buffer has read it
+        __syncwarp();
         tmem_ld_wait();
-        if (c0 + 32 < p.cout) tmem_ld32(taddr + c0 + 32, vb);
-        epilogue_chunk(va, s_shift + c0, optr + c0, ok);
-        if (c0 + 32 < p.cout) {
-          tmem_ld_wait();
-          if (c0 + 64 < p.cout) tmem_ld32(taddr + c0 + 64, va);
-          epilogue_chunk(vb, s_shift + c0 + 32, optr + c0 + 32, ok);
+        tmem_ld32(taddr + c0 + 32, vb);
+        epilogue_chunk(va, s_shift + c0, row_base, 0, lane & 7);
+        tmem_ld_wait();
+        if (c0 + 64 < p.cout) tmem_ld32(taddr + c0 + 64, va);
+        epilogue_chunk(vb, s_shift + c0 + 32, row_base, 4, lane & 7);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (kConv1) tma_store_3d(&p.tmap_out, c0, row0, rv, box);
+          else tma_store_2d(&p.tmap_out, c0, row0, box);
+          bulk_commit_group();
         }
+        obuf ^= 1;
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[acc]);
       if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) bulk_wait_group_all();
   } else if (warp == MMA_WARP) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
@@ -415,7 +466,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       int rs = 0; uint32_t pr = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int m0 = tile * TILE_M;
-        const int v0 = m0 / p.t_out, t0 = m0 - v0 * p.t_out;
+        const int v0 = div_t_out(p, m0), t0 = m0 - v0 * p.t_out;
         const int lo = v0 * p.t_in + t0 * kStride - p.pad_left;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&raw_empty[rs], pr ^ 1);
@@ -514,17 +565,21 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// [rows, cin] fp16 row-major activation, box = [box_rows, 64 channels], dense 128-byte rows in smem
-int make_act_tensor_map(kws_handle* h, CUtensorMap* tm, const __half* act, long long rows, int cin, int box_rows) {
+// fp16 channels-last activation [d2][d1][c] (d2 = 1 for a plain [rows, c] matrix); box = [1][box_rows][64 ch]
+int make_tensor_map(kws_handle* h, CUtensorMap* tm, const __half* act, int c, long long d1, long long d2,
+                    int box_rows, bool swizzle128) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return fail(h, KWS_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
-  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cin), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cin) * sizeof(__half)};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(SLAB_K), static_cast<cuuint32_t>(box_rows)};
-  const cuuint32_t estride[2] = {1, 1};
-  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(act), gdim, gstride, box, estride,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const cuuint32_t rank = d2 > 1 ? 3 : 2;
+  const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(d1), static_cast<cuuint64_t>(d2)};
+  const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(c) * sizeof(__half),
+                                 static_cast<cuuint64_t>(c) * sizeof(__half) * static_cast<cuuint64_t>(d1)};
+  const cuuint32_t box[3] = {static_cast<cuuint32_t>(SLAB_K), static_cast<cuuint32_t>(box_rows), 1};
+  const cuuint32_t estride[3] = {1, 1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<__half*>(act), gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(h, KWS_ECUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(r));
   return KWS_OK;
 }
@@ -540,34 +595,28 @@ int launch_tc_gemm(kws_handle* h, GemmParams& p, cudaStream_t st) {
   p.acc_stages = std::min(2, TMEM_COLS / p.cout);
   p.a_stage_bytes = conv1 ? 2 * A_SLAB_BYTES : A_SLAB_BYTES;
   const int blocks = p.num_kb * p.n_halves;
-  const int raw_min = conv1 ? 0 : (MODE == 1 ? 3 : 2);
-  const int raw_max = conv1 ? 0 : 6;
   auto fits = [&](int a, int b, int r) {
     p.a_stages = a; p.b_stages = b; p.raw_stages = r;
     return static_cast<int>(smem_layout(p, conv1).total) <= SMEM_LIMIT;
   };
-  auto best_raw = [&](int a, int b) {          // deepest raw ring that fits, -1 if below the minimum
-    for (int r = raw_max; r >= raw_min; --r)
-      if (fits(a, b, r)) return r;
-    return -1;
-  };
   bool chosen = false;
-  const int a_try[3] = {conv1 ? 3 : 4, 3, 2};
-  // weights resident in smem when they fit next to the rings, else a streaming ring of blocks
-  if (blocks <= MAX_B_BLOCKS) {
-    for (int ai = 0; ai < 2 && !chosen; ++ai) {
-      const int r = best_raw(a_try[ai], blocks);
-      if (r >= 0) { fits(a_try[ai], blocks, r); p.b_resident = 1; chosen = true; }
-    }
-  }
-  if (!chosen) {
-    p.b_resident = 0;
+  if (conv1) {
+    p.b_resident = 1;
+    chosen = fits(3, blocks, 0) || fits(2, blocks, 0);
+  } else {
+    // The two producer groups work on alternate slabs, so the A and raw rings need EVEN depths: with
+    // slot = n % depth every slot then belongs to one group, and no thread ever waits on an mbarrier
+    // more than one phase ahead of it (a group that skipped a slot's previous use would otherwise
+    // see a stale parity).  Preference: weights resident, deep A ring, then deep raw ring.
     const int b_block = p.n_inst * ROW_BYTES;
-    const int b_try[3] = {std::max(2, std::min(4, 65536 / b_block)), 3, 2};
-    for (int bi = 0; bi < 3 && !chosen; ++bi)
-      for (int ai = 0; ai < 3 && !chosen; ++ai) {
-        const int r = best_raw(a_try[ai], b_try[bi]);
-        if (r >= 0) { fits(a_try[ai], b_try[bi], r); chosen = true; }
+    const int b_stream = std::max(2, std::min(4, 65536 / b_block));
+    const int r_min = MODE == 1 ? 4 : 2;
+    for (int a = 4; a >= 2 && !chosen; a -= 2)
+      for (int res = 1; res >= 0 && !chosen; --res) {
+        if (res && blocks > MAX_B_BLOCKS) continue;
+        for (int bs = res ? blocks : b_stream; bs >= (res ? blocks : 2) && !chosen; --bs)
+          for (int r = 6; r >= r_min && !chosen; r -= 2)
+            if (fits(a, bs, r)) { p.b_resident = res; chosen = true; }
       }
   }
   if (!chosen) return fail(h, KWS_EUNSUPPORTED, "layer does not fit in shared memory");
@@ -582,6 +631,12 @@ int launch_tc_gemm(kws_handle* h, GemmParams& p, cudaStream_t st) {
   KWS_T0(h, MODE == 0 ? KC_CONV1 : KC_BLOCKS, st);
   tc_gemm_kernel<MODE><<<grid, TC_THREADS, lay.total, st>>>(p);
   KWS_T1(h, st);
+  if (debug_sync() && cudaDeviceSynchronize() != cudaSuccess)
+    return fail(h, KWS_ECUDA, "tc_gemm_kernel<" + std::to_string(MODE) + "> cin " + std::to_string(p.cin) + " cout " +
+                                  std::to_string(p.cout) + " rows_out " + std::to_string(p.rows_out) + " stages a/b/raw " +
+                                  std::to_string(p.a_stages) + "/" + std::to_string(p.b_stages) + "/" +
+                                  std::to_string(p.raw_stages) + " resident " + std::to_string(p.b_resident) + ": " +
+                                  cudaGetErrorString(cudaGetLastError()));
   KWS_LAUNCH_CHECK(h);
   return KWS_OK;
 }
@@ -642,12 +697,14 @@ int launch_forward_tc(kws_handle* h, Model& m, const float* wav, int B, const Vi
       GemmParams p{};
       p.wav = wav + static_cast<size_t>(b0) * L; p.vt = vt; p.n_views = V;
       p.w_img = reinterpret_cast<const uint8_t*>(m.tc_conv1);
-      p.shift = m.bn_shift[0]; p.out = cur;
+      p.shift = m.bn_shift[0];
       p.cin = CONV1_K; p.cout = m.c0; p.t_out = m.t0; p.rows_out = rows * m.t0;
       p.tiles_per_group = (m.t0 + TILE_M - 1) / TILE_M;
       p.num_tiles = rows * p.tiles_per_group;
       p.num_kb = 2; p.last_ksteps = 1;
-      int rc = launch_tc_gemm<0>(h, p, st);
+      int rc = make_tensor_map(h, &p.tmap_out, cur, m.c0, m.t0, std::max(rows, 2), 32, true);   // 3-D: clip at t0
+      if (rc) return rc;
+      rc = launch_tc_gemm<0>(h, p, st);
       if (rc) return rc;
     }
     if (dbg_layer == 0) return launch_to_float(h, cur, true, dbg_out, static_cast<size_t>(rows) * m.t0 * m.c0, st);
@@ -657,20 +714,23 @@ int launch_forward_tc(kws_handle* h, Model& m, const float* wav, int B, const Vi
       GemmParams p{};
       p.dw_h = m.tc_dw[i];
       p.w_img = reinterpret_cast<const uint8_t*>(m.tc_pw[i]);
-      p.shift = m.bn_shift[i + 1]; p.out = nxt;
+      p.shift = m.bn_shift[i + 1];
       p.cin = d.cin; p.cout = d.cout; p.stride = d.stride; p.pad_left = d.pad_left;
       p.t_in = d.t_in; p.t_out = d.t_out; p.rows_out = rows * d.t_out;
       p.num_tiles = (p.rows_out + TILE_M - 1) / TILE_M;
       p.num_kb = d.cin / SLAB_K; p.last_ksteps = 4;
-      p.box_rows = d.stride == 1 ? RAW_BOX_S1 : RAW_BOX_S2;
-      p.n_boxes = d.stride == 1 ? 1 : 2;
-      p.raw_stage_bytes = p.box_rows * p.n_boxes * ROW_BYTES;
-      // worst-case extent of a tile inside the raw box: 127 rows * stride + one jump per clip boundary + 3 taps
+      // extent of a tile inside the raw box: 127 rows * stride + one jump per clip boundary + 3 taps
+      // (stride 2: a boundary advances by t_in - 2 t_out + 2 <= 2 rows, no more than a normal step)
       const int boundaries = (TILE_M + d.t_out - 2) / d.t_out;
-      const int jump = d.stride == 1 ? 2 : 0;   // stride 2: a boundary advances by t_in - 2 t_out + 2 <= 2 rows
-      if ((TILE_M - 1) * d.stride + boundaries * jump + 3 > p.box_rows * p.n_boxes)
-        return fail(h, KWS_EUNSUPPORTED, "tile does not fit the raw activation box");
-      int rc = make_act_tensor_map(h, &p.tmap_in, cur, static_cast<long long>(rows) * d.t_in, d.cin, p.box_rows);
+      const int extent = (TILE_M - 1) * d.stride + (d.stride == 1 ? 2 * boundaries : 0) + 3;
+      p.n_boxes = d.stride == 1 ? 1 : 2;
+      p.box_rows = ((extent + p.n_boxes - 1) / p.n_boxes + 7) & ~7;
+      if (p.box_rows > 256) return fail(h, KWS_EUNSUPPORTED, "tile does not fit the raw activation box");
+      p.raw_stage_bytes = p.box_rows * p.n_boxes * ROW_BYTES;
+      p.t_out_magic = ((1ull << 40) + d.t_out - 1) / d.t_out;
+      int rc = make_tensor_map(h, &p.tmap_in, cur, d.cin, static_cast<long long>(rows) * d.t_in, 1, p.box_rows, false);
+      if (rc) return rc;
+      rc = make_tensor_map(h, &p.tmap_out, nxt, d.cout, static_cast<long long>(rows) * d.t_out, 1, 32, true);
       if (rc) return rc;
       rc = d.stride == 1 ? launch_tc_gemm<1>(h, p, st) : launch_tc_gemm<2>(h, p, st);
       if (rc) return rc;
