@@ -140,6 +140,13 @@ void kws_destroy(kws_t* h) {
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->stage_d) cudaFree(h->stage_d);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+  if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+    if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
+    if (h->ev_d2h[i]) cudaEventDestroy(h->ev_d2h[i]);
+  }
   for (auto& t : h->timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
   for (auto e : h->event_pool) cudaEventDestroy(e);
   delete h;
@@ -289,9 +296,9 @@ int kws_vote(kws_t* h, const int32_t* labels, int M, int B, int min_count, int32
 }
 
 // ------------------------------------------------------------------------------------------
-// Host-buffer entry points.  One staging allocation on the device holds, per call, the
-// waveforms, parameters and results; copies and kernels are enqueued on the handle's own
-// stream in chunks so the H2D copy of chunk k+1 queues behind the kernels of chunk k.
+// Host-buffer entry points.  One staging allocation on the device holds two slots of
+// waveforms, parameters and results; H2D copies, kernels and D2H copies of consecutive chunks
+// run on three streams ordered by per-slot events, so the copies hide under the kernels.
 // Pinned caller buffers make the copies truly asynchronous; pageable ones still work.
 // ------------------------------------------------------------------------------------------
 struct StageLayout {
@@ -338,59 +345,88 @@ int kws_pipeline_host(kws_t* h, int slot, const float* wav_h, const int32_t* shi
     classes = h->models[slot].classes;
   }
   const size_t fdim = do_feat ? feat_dim(h, feat_kind) : 0;
-  const int chunk = std::max(1, std::min(B, do_fwd ? std::max(1, h->max_rows / n_views) * 4 : 8192));
+  // Chunks of one forward pass worth of clip-views (max_rows), so that with two staging slots
+  // the H2D copy of chunk k+1 (copy stream) and the D2H copy of chunk k-1 (second copy stream)
+  // run under the kernels of chunk k (compute stream); events order the three streams per slot.
+  const int chunk = std::max(1, std::min(std::min(B, 2048), do_fwd ? std::max(1, h->max_rows / n_views) : 2048));
   const StageLayout lay = stage_layout(h, chunk, std::max(classes, 1), fdim);
-  // two staging slots so the copy of the next chunk can be queued while this one computes
   int rc = ensure_bytes(h, &h->stage_d, &h->stage_bytes, 2 * lay.total);
   if (rc) return rc;
-  cudaStream_t st = h->own_stream;
+  if (!h->h2d_stream) {
+    KWS_CUDA(h, cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+    KWS_CUDA(h, cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      KWS_CUDA(h, cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+      KWS_CUDA(h, cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
+      KWS_CUDA(h, cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming));
+    }
+  }
+  cudaStream_t st = h->own_stream, s_in = h->h2d_stream, s_out = h->d2h_stream;
   int k = 0;
   for (int b0 = 0; b0 < B; b0 += chunk, ++k) {
     const int nb = std::min(chunk, B - b0);
-    char* base = static_cast<char*>(h->stage_d) + (k & 1) * lay.total;
+    const int slot_k = k & 1;
+    char* base = static_cast<char*>(h->stage_d) + slot_k * lay.total;
     float* d_wav = reinterpret_cast<float*>(base + lay.wav);
     float* d_aug = reinterpret_cast<float*>(base + lay.aug);
+    // ---- copy stream: inputs of chunk k (its slot was last read by the kernels of chunk k-2) ----
+    if (k >= 2) KWS_CUDA(h, cudaStreamWaitEvent(s_in, h->ev_comp[slot_k], 0));
     KWS_CUDA(h, cudaMemcpyAsync(d_wav, wav_h + static_cast<size_t>(b0) * L, static_cast<size_t>(nb) * L * 4,
-                                cudaMemcpyHostToDevice, st));
+                                cudaMemcpyHostToDevice, s_in));
+    int32_t* d_shift = reinterpret_cast<int32_t*>(base + lay.shift);
+    int32_t* d_bgf = reinterpret_cast<int32_t*>(base + lay.bgf);
+    int32_t* d_bgo = reinterpret_cast<int32_t*>(base + lay.bgo);
+    float* d_bgv = reinterpret_cast<float*>(base + lay.bgv);
+    float* d_fgv = reinterpret_cast<float*>(base + lay.fgv);
+    if (do_aug) {
+      KWS_CUDA(h, cudaMemcpyAsync(d_shift, shift_h + b0, nb * 4, cudaMemcpyHostToDevice, s_in));
+      KWS_CUDA(h, cudaMemcpyAsync(d_bgf, bg_file_h + b0, nb * 4, cudaMemcpyHostToDevice, s_in));
+      KWS_CUDA(h, cudaMemcpyAsync(d_bgo, bg_off_h + b0, nb * 4, cudaMemcpyHostToDevice, s_in));
+      KWS_CUDA(h, cudaMemcpyAsync(d_bgv, bg_vol_h + b0, nb * 4, cudaMemcpyHostToDevice, s_in));
+      KWS_CUDA(h, cudaMemcpyAsync(d_fgv, fg_vol_h + b0, nb * 4, cudaMemcpyHostToDevice, s_in));
+    }
+    KWS_CUDA(h, cudaEventRecord(h->ev_h2d[slot_k], s_in));
+    // ---- compute stream: kernels of chunk k (its result buffers were last read by D2H of chunk k-2) ----
+    KWS_CUDA(h, cudaStreamWaitEvent(st, h->ev_h2d[slot_k], 0));
+    if (k >= 2) KWS_CUDA(h, cudaStreamWaitEvent(st, h->ev_d2h[slot_k], 0));
     const float* x = d_wav;
     if (do_aug) {
-      int32_t* d_shift = reinterpret_cast<int32_t*>(base + lay.shift);
-      int32_t* d_bgf = reinterpret_cast<int32_t*>(base + lay.bgf);
-      int32_t* d_bgo = reinterpret_cast<int32_t*>(base + lay.bgo);
-      float* d_bgv = reinterpret_cast<float*>(base + lay.bgv);
-      float* d_fgv = reinterpret_cast<float*>(base + lay.fgv);
-      KWS_CUDA(h, cudaMemcpyAsync(d_shift, shift_h + b0, nb * 4, cudaMemcpyHostToDevice, st));
-      KWS_CUDA(h, cudaMemcpyAsync(d_bgf, bg_file_h + b0, nb * 4, cudaMemcpyHostToDevice, st));
-      KWS_CUDA(h, cudaMemcpyAsync(d_bgo, bg_off_h + b0, nb * 4, cudaMemcpyHostToDevice, st));
-      KWS_CUDA(h, cudaMemcpyAsync(d_bgv, bg_vol_h + b0, nb * 4, cudaMemcpyHostToDevice, st));
-      KWS_CUDA(h, cudaMemcpyAsync(d_fgv, fg_vol_h + b0, nb * 4, cudaMemcpyHostToDevice, st));
       rc = launch_augment(h, d_wav, nullptr, 1.0f, d_shift, d_bgf, d_bgo, d_bgv, d_fgv, d_aug, nb, 0, st);
       if (rc) return rc;
       x = d_aug;
     }
+    float* d_feat = reinterpret_cast<float*>(base + lay.feat);
+    float* d_probs = reinterpret_cast<float*>(base + lay.probs);
+    int32_t* d_amax = reinterpret_cast<int32_t*>(base + lay.amax);
     if (do_feat) {
-      float* d_feat = reinterpret_cast<float*>(base + lay.feat);
       rc = features_dispatch(h, x, nb, feat_kind, d_feat, st);
       if (rc) return rc;
-      if (feat_h)
-        KWS_CUDA(h, cudaMemcpyAsync(feat_h + static_cast<size_t>(b0) * fdim, d_feat, static_cast<size_t>(nb) * fdim * 4,
-                                    cudaMemcpyDeviceToHost, st));
-    } else if (feat_h && !do_fwd) {                      // 'raw' representation: the augmented waveform
-      KWS_CUDA(h, cudaMemcpyAsync(feat_h + static_cast<size_t>(b0) * L, x, static_cast<size_t>(nb) * L * 4,
-                                  cudaMemcpyDeviceToHost, st));
     }
     if (do_fwd) {
-      float* d_probs = reinterpret_cast<float*>(base + lay.probs);
-      int32_t* d_amax = reinterpret_cast<int32_t*>(base + lay.amax);
       rc = forward_dispatch(h, slot, x, nb, vt, d_probs, d_amax, st);
       if (rc) return rc;
+    }
+    KWS_CUDA(h, cudaEventRecord(h->ev_comp[slot_k], st));
+    // ---- second copy stream: results of chunk k ----
+    KWS_CUDA(h, cudaStreamWaitEvent(s_out, h->ev_comp[slot_k], 0));
+    if (do_feat) {
+      if (feat_h)
+        KWS_CUDA(h, cudaMemcpyAsync(feat_h + static_cast<size_t>(b0) * fdim, d_feat, static_cast<size_t>(nb) * fdim * 4,
+                                    cudaMemcpyDeviceToHost, s_out));
+    } else if (feat_h && !do_fwd) {                      // 'raw' representation: the augmented waveform
+      KWS_CUDA(h, cudaMemcpyAsync(feat_h + static_cast<size_t>(b0) * L, x, static_cast<size_t>(nb) * L * 4,
+                                  cudaMemcpyDeviceToHost, s_out));
+    }
+    if (do_fwd) {
       if (probs_h)
         KWS_CUDA(h, cudaMemcpyAsync(probs_h + static_cast<size_t>(b0) * classes, d_probs,
-                                    static_cast<size_t>(nb) * classes * 4, cudaMemcpyDeviceToHost, st));
+                                    static_cast<size_t>(nb) * classes * 4, cudaMemcpyDeviceToHost, s_out));
       if (argmax_h)
-        KWS_CUDA(h, cudaMemcpyAsync(argmax_h + b0, d_amax, nb * 4, cudaMemcpyDeviceToHost, st));
+        KWS_CUDA(h, cudaMemcpyAsync(argmax_h + b0, d_amax, nb * 4, cudaMemcpyDeviceToHost, s_out));
     }
+    KWS_CUDA(h, cudaEventRecord(h->ev_d2h[slot_k], s_out));
   }
+  KWS_CUDA(h, cudaStreamSynchronize(s_out));
   KWS_CUDA(h, cudaStreamSynchronize(st));
   return KWS_OK;
 }

@@ -93,7 +93,9 @@ struct kws_handle {
   // host-entry staging
   void* pinned = nullptr;  size_t pinned_bytes = 0;
   void* stage_d = nullptr; size_t stage_bytes = 0;
-  cudaStream_t own_stream = nullptr;
+  cudaStream_t own_stream = nullptr;      // compute stream of the host entry points
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   // optional per-kernel-class device timing (bench.py roofline): event pairs around launches
   bool timing = false;
   struct TimedLaunch { int cls; cudaEvent_t e0, e1; };

@@ -1,11 +1,11 @@
-// K7 head -- attention pooling + classifier + TTA mean + argmax, one CTA per clip.
+// K7 head -- attention pooling + classifier + TTA mean + argmax, one warp per clip-view.
 // Replaces, per view (reference model.py:819-830):
 //   Flatten -> Dense(T, softmax) -> x * a[:, None] -> GlobalMaxPool1D || GlobalAveragePooling1D
 //   -> Dense(classes, softmax)            (exp 195/206)
 //   Flatten -> Dense(T, softmax, no bias) -> mean_t(x * a) -> Dense(32, softmax)   (exp 106)
 // and across views (make_submission.py:137-146): probs = (p_0 + p_1 + ...) / n_views in view
 // order, argmax with first-index tie rule.  Memory/latency-bound CUDA-core work with
-// warp-shuffle reductions; the weights (166 KB + 48 KB) stay L2/L1-resident.
+// warp-shuffle reductions; the weights (166 KB + 48 KB) are shared-memory resident.
 #include <algorithm>
 
 #include "common.cuh"
@@ -14,7 +14,6 @@ namespace kws {
 
 namespace {
 
-constexpr int HEAD_THREADS = 256;
 constexpr int HEAD_T = 9;                 // time steps entering the head (both shipped archs)
 constexpr int HEAD_MAX_CLASSES = 32;
 
@@ -32,101 +31,135 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Persistent kernel: the dense_1 (166 KB) and dense_2 (48 KB, transposed) weights live in shared
+// memory for the whole launch -- re-fetching them per clip-view from L2 is what bounds a
+// one-CTA-per-clip formulation -- and every warp owns one (clip, view) at a time: lane-strided dot
+// products (bank-conflict-free: the row stride of dense_1 is 9 words), warp-shuffle reductions,
+// pooled features in registers.  A CTA iteration covers floor(16 / n_views) clips; the per-view
+// probabilities meet in shared memory and are averaged in view order.
+constexpr int HEAD_WARPS = 16;
+constexpr int HEAD_CH_PER_LANE = 16;              // channels per lane in the pooling: C <= 512
+
 template <typename TAct>
-__global__ void __launch_bounds__(HEAD_THREADS)
-head_kernel(const TAct* __restrict__ act, int C, int n_views, const float* __restrict__ w_d1,
+__global__ void __launch_bounds__(HEAD_WARPS * 32, 1)
+head_kernel(const TAct* __restrict__ act, int C, int n_views, int n_clips, const float* __restrict__ w_d1,
             const float* __restrict__ b_d1, const float* __restrict__ w_d2, int classes,
             int pool_max_avg, float* __restrict__ probs_mean, int32_t* __restrict__ argmax) {
   extern __shared__ float sm[];
-  float* xs = sm;                               // [HEAD_T * C]
-  float* z = xs + HEAD_T * C;                   // [2*C]
-  float* red = z + 2 * C;                       // [8 warps][HEAD_T]
-  float* att = red + (HEAD_THREADS / 32) * HEAD_T;   // [HEAD_T]
-  float* logits = att + 16;                     // [HEAD_MAX_CLASSES]
-
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = HEAD_T * C;
   const int feat = pool_max_avg ? 2 * C : C;
-  float acc_p = 0.0f;                           // warp 0, lane j: running sum of class j
+  float* w1 = sm;                                       // [n][HEAD_T]
+  float* w2t = w1 + n * HEAD_T;                         // [classes][feat]
+  float* pv = w2t + classes * feat;                     // [HEAD_WARPS][32] per-view probabilities
 
-  for (int v = 0; v < n_views; ++v) {
-    const TAct* x = act + (static_cast<size_t>(b) * n_views + v) * n;
-    float p[HEAD_T];
-#pragma unroll
-    for (int j = 0; j < HEAD_T; ++j) p[j] = 0.0f;
-    for (int i = tid; i < n; i += HEAD_THREADS) {
-      const float xv = to_float(x[i]);
-      xs[i] = xv;
-      const float* wr = w_d1 + static_cast<size_t>(i) * HEAD_T;
-#pragma unroll
-      for (int j = 0; j < HEAD_T; ++j) p[j] = fmaf(xv, __ldg(&wr[j]), p[j]);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  {
+    const float4* src = reinterpret_cast<const float4*>(w_d1);
+    float4* dst = reinterpret_cast<float4*>(w1);
+    for (int i = tid; i < n * HEAD_T / 4; i += HEAD_WARPS * 32) dst[i] = __ldg(&src[i]);
+    for (int i = tid; i < feat * classes; i += HEAD_WARPS * 32) {
+      const int r = i / classes, j = i - r * classes;
+      w2t[j * feat + r] = __ldg(&w_d2[i]);
     }
-#pragma unroll
-    for (int j = 0; j < HEAD_T; ++j) {
-      const float s = warp_sum(p[j]);
-      if (lane == 0) red[warp * HEAD_T + j] = s;
-    }
-    __syncthreads();
-    if (warp == 0) {                            // attention softmax over T (dense_1)
-      float l = -INFINITY;
-      if (lane < HEAD_T) {
-        l = __ldg(&b_d1[lane]);
-#pragma unroll
-        for (int w = 0; w < HEAD_THREADS / 32; ++w) l += red[w * HEAD_T + lane];
-      }
-      const float mx = warp_max(l);
-      const float e = lane < HEAD_T ? expf(l - mx) : 0.0f;
-      const float s = warp_sum(e);
-      if (lane < HEAD_T) att[lane] = __fdiv_rn(e, s);
-    }
-    __syncthreads();
-    for (int c = tid; c < C; c += HEAD_THREADS) {
-      float mx = -INFINITY, sum_x = 0.0f, sum_w = 0.0f;
-#pragma unroll
-      for (int t = 0; t < HEAD_T; ++t) {
-        const float xv = xs[t * C + c];
-        const float wv = __fmul_rn(xv, att[t]);          // multiply_1
-        mx = fmaxf(mx, wv);
-        sum_x += xv;
-        sum_w += wv;
-      }
-      if (pool_max_avg) {
-        z[c] = mx;                                       // global_max_pooling1d_1(x * a)
-        z[C + c] = __fdiv_rn(sum_x, static_cast<float>(HEAD_T));   // global_average_pooling1d_1(x)
-      } else {
-        z[c] = __fdiv_rn(sum_w, static_cast<float>(HEAD_T));       // exp 106: mean_t(x * a)
-      }
-    }
-    __syncthreads();
-    for (int j = warp; j < classes; j += HEAD_THREADS / 32) {     // dense_2
-      float s = 0.0f;
-      for (int i = lane; i < feat; i += 32) s = fmaf(z[i], __ldg(&w_d2[static_cast<size_t>(i) * classes + j]), s);
-      s = warp_sum(s);
-      if (lane == 0) logits[j] = s;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      const float l = lane < classes ? logits[lane] : -INFINITY;
-      const float mx = warp_max(l);
-      const float e = lane < classes ? expf(l - mx) : 0.0f;
-      const float s = warp_sum(e);
-      acc_p = __fadd_rn(acc_p, __fdiv_rn(e, s));         // probs + loud_probs + left_probs ...
-    }
-    __syncthreads();
   }
-  if (warp == 0) {
-    const float pm = __fdiv_rn(acc_p, static_cast<float>(n_views));   // ... / 3
-    if (probs_mean && lane < classes) probs_mean[static_cast<size_t>(b) * classes + lane] = pm;
-    // probs.argmax(axis=-1): first index among equal maxima
-    float best = lane < classes ? pm : -INFINITY;
-    int idx = lane < classes ? lane : 0x7fffffff;
+  const float bias = lane < HEAD_T ? __ldg(&b_d1[lane]) : 0.0f;
+  __syncthreads();
+
+  const int cpi = HEAD_WARPS / n_views;                 // clips per CTA iteration (n_views <= 16)
+  const int ci = warp / n_views, v = warp - ci * n_views;
+  for (int clip0 = blockIdx.x * cpi; clip0 < n_clips; clip0 += gridDim.x * cpi) {
+    const int clip = clip0 + ci;
+    if (ci < cpi && clip < n_clips) {
+      const TAct* x = act + (static_cast<size_t>(clip) * n_views + v) * n;
+      // ---- dense_1 + softmax over T ----
+      float p[HEAD_T];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-      if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+      for (int j = 0; j < HEAD_T; ++j) p[j] = 0.0f;
+#pragma unroll 4
+      for (int i = lane; i < n; i += 32) {
+        const float xv = to_float(x[i]);
+        const float* wr = w1 + i * HEAD_T;
+#pragma unroll
+        for (int j = 0; j < HEAD_T; ++j) p[j] = fmaf(xv, wr[j], p[j]);
+      }
+      float l = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < HEAD_T; ++j) {
+        const float s = warp_sum(p[j]);
+        if (lane == j) l = s + bias;
+      }
+      float mx = warp_max(l);
+      float e = lane < HEAD_T ? expf(l - mx) : 0.0f;
+      float s = warp_sum(e);
+      const float a = __fdiv_rn(e, s);                   // lane t holds att[t]
+      float att[HEAD_T];
+#pragma unroll
+      for (int t = 0; t < HEAD_T; ++t) att[t] = __shfl_sync(0xffffffffu, a, t);
+      // ---- multiply_1 + pooling: lane owns channels lane, lane + 32, ... ----
+      float z0[HEAD_CH_PER_LANE], z1[HEAD_CH_PER_LANE];
+#pragma unroll
+      for (int k = 0; k < HEAD_CH_PER_LANE; ++k) {
+        const int c = lane + 32 * k;
+        z0[k] = 0.0f; z1[k] = 0.0f;
+        if (c < C) {
+          float m = -INFINITY, sum_x = 0.0f, sum_w = 0.0f;
+#pragma unroll
+          for (int t = 0; t < HEAD_T; ++t) {
+            const float xv = to_float(x[t * C + c]);
+            const float wv = __fmul_rn(xv, att[t]);          // multiply_1
+            m = fmaxf(m, wv);
+            sum_x += xv;
+            sum_w += wv;
+          }
+          if (pool_max_avg) {
+            z0[k] = m;                                       // global_max_pooling1d_1(x * a)
+            z1[k] = __fdiv_rn(sum_x, static_cast<float>(HEAD_T));   // global_average_pooling1d_1(x)
+          } else {
+            z0[k] = __fdiv_rn(sum_w, static_cast<float>(HEAD_T));   // exp 106: mean_t(x * a)
+          }
+        }
+      }
+      // ---- dense_2 + softmax ----
+      l = -INFINITY;
+      for (int j = 0; j < classes; ++j) {
+        const float* wc = w2t + j * feat;
+        float d = 0.0f;
+#pragma unroll
+        for (int k = 0; k < HEAD_CH_PER_LANE; ++k) {
+          const int c = lane + 32 * k;
+          if (c < C) {
+            d = fmaf(z0[k], wc[c], d);
+            if (pool_max_avg) d = fmaf(z1[k], wc[C + c], d);
+          }
+        }
+        d = warp_sum(d);
+        if (lane == j) l = d;
+      }
+      mx = warp_max(l);
+      e = lane < classes ? expf(l - mx) : 0.0f;
+      s = warp_sum(e);
+      pv[warp * 32 + lane] = __fdiv_rn(e, s);
     }
-    if (argmax && lane == 0) argmax[b] = idx;
+    __syncthreads();
+    if (warp < cpi && clip0 + warp < n_clips) {           // warp w averages the views of clip clip0 + w
+      const int b = clip0 + warp;
+      float acc_p = 0.0f;
+      for (int u = 0; u < n_views; ++u)
+        acc_p = __fadd_rn(acc_p, pv[(warp * n_views + u) * 32 + lane]);   // probs + loud_probs + left_probs ...
+      const float pm = __fdiv_rn(acc_p, static_cast<float>(n_views));   // ... / 3
+      if (probs_mean && lane < classes) probs_mean[static_cast<size_t>(b) * classes + lane] = pm;
+      // probs.argmax(axis=-1): first index among equal maxima
+      float best = lane < classes ? pm : -INFINITY;
+      int idx = lane < classes ? lane : 0x7fffffff;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+      }
+      if (argmax && lane == 0) argmax[b] = idx;
+    }
+    __syncthreads();
   }
 }
 
@@ -154,17 +187,29 @@ int launch_head(kws_handle* h, Model& m, const void* act, bool act_half, int n_c
                 float* probs_mean, int32_t* argmax, cudaStream_t st) {
   if (m.t_last != HEAD_T) return fail(h, KWS_EUNSUPPORTED, "head expects 9 time steps");
   if (m.classes > HEAD_MAX_CLASSES) return fail(h, KWS_EUNSUPPORTED, "too many classes");
+  if (n_views < 1 || n_views > HEAD_WARPS) return fail(h, KWS_EINVAL, "n_views must be in 1..16");
   const int C = m.c_last;
-  const size_t smem = (static_cast<size_t>(HEAD_T) * C + 2 * C + (HEAD_THREADS / 32) * HEAD_T + 16 +
-                       HEAD_MAX_CLASSES) * sizeof(float);
+  if (C > 32 * HEAD_CH_PER_LANE || C % 4) return fail(h, KWS_EUNSUPPORTED, "head expects at most 512 channels");
+  const int feat = m.pool_max_avg ? 2 * C : C;
+  const size_t smem = (static_cast<size_t>(HEAD_T) * C * HEAD_T + static_cast<size_t>(m.classes) * feat +
+                       HEAD_WARPS * 32) * sizeof(float);
+  if (smem > 227 * 1024) return fail(h, KWS_EUNSUPPORTED, "head weights do not fit in shared memory");
+  static bool attr_set = false;
+  if (!attr_set) {
+    KWS_CUDA(h, cudaFuncSetAttribute(head_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    KWS_CUDA(h, cudaFuncSetAttribute(head_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int cpi = HEAD_WARPS / n_views;
+  const int grid = std::max(1, std::min(h->num_sms, (n_clips + cpi - 1) / cpi));
   KWS_T0(h, KC_HEAD, st);
   if (act_half) {
-    head_kernel<__half><<<n_clips, HEAD_THREADS, smem, st>>>(
-        static_cast<const __half*>(act), C, n_views, m.w_d1, m.b_d1, m.w_d2, m.classes,
+    head_kernel<__half><<<grid, HEAD_WARPS * 32, smem, st>>>(
+        static_cast<const __half*>(act), C, n_views, n_clips, m.w_d1, m.b_d1, m.w_d2, m.classes,
         m.pool_max_avg ? 1 : 0, probs_mean, argmax);
   } else {
-    head_kernel<float><<<n_clips, HEAD_THREADS, smem, st>>>(
-        static_cast<const float*>(act), C, n_views, m.w_d1, m.b_d1, m.w_d2, m.classes,
+    head_kernel<float><<<grid, HEAD_WARPS * 32, smem, st>>>(
+        static_cast<const float*>(act), C, n_views, n_clips, m.w_d1, m.b_d1, m.w_d2, m.classes,
         m.pool_max_avg ? 1 : 0, probs_mean, argmax);
   }
   KWS_T1(h, st);

@@ -55,7 +55,19 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int CONV1_K = 80;                                      // samples per output row
 constexpr int CONV1_ROW_HOP = 40;
 constexpr int CONV1_WIN = CONV1_ROW_HOP * (TILE_M - 1) + CONV1_K;   // 5160 staged samples per tile
+constexpr uint32_t CONV1_WIN_BYTES = ((CONV1_WIN + 8) * 2 + 15) & ~15;   // one fp16 window buffer
+constexpr int CONV1_QUADS = 6;                                   // float4 loads per producer thread and tile
 
+
+// TTA views that share a roll shift differ only by the gain, and conv1d_1 is linear and bias-free
+// (model.py:68-74), so they share the A tile and the accumulator: gain * conv(x) == conv(gain * x).
+struct ViewGroups {
+  int n_groups;
+  int shift[KWS_MAX_VIEWS];       // roll shift of the group, already reduced to [0, L)
+  int start[KWS_MAX_VIEWS + 1];   // members of group g = [start[g], start[g+1])
+  int view[KWS_MAX_VIEWS];        // member -> view index (output row block)
+  float gain[KWS_MAX_VIEWS];      // member -> gain
+};
 
 struct alignas(64) GemmParams {
   CUtensorMap tmap_in;      // dw_pw: previous activation [rows_in, cin] fp16, box [box_rows, 64]
@@ -63,8 +75,8 @@ struct alignas(64) GemmParams {
                             // [rows_out, cout]; conv1: 3-D [clip-views, t_out, cout] (rows clipped per view)
   // conv1 A side
   const float* wav;         // waveforms [B, 16000] fp32
-  ViewTable vt;             // TTA views
-  int n_views;
+  ViewGroups vg;            // TTA views grouped by shift: one staged window + one MMA per (clip, group),
+  int n_views;              // one epilogue pass per member view (the gain is applied to the accumulator)
   // dw_pw A side
   const __half* dw_h;       // depthwise taps [3][cin] fp16
   // B side: pre-swizzled fp16 blocks of n_inst rows x 128 B, block j = (kb, nh) = (j / n_halves, j % n_halves)
@@ -103,7 +115,7 @@ __host__ __device__ inline SmemLayout smem_layout(const GemmParams& p, bool conv
   // aux: shift[cout] fp32, then (dw_pw) taps [3*cin] fp16 + row metadata [2 groups][2 parities][128] u32
   //      or (conv1) the staged fp16 waveform window
   o += static_cast<uint32_t>(p.cout) * 4u;
-  o += conv1 ? static_cast<uint32_t>(((CONV1_WIN + 8) * 2 + 15) & ~15)
+  o += conv1 ? 2u * CONV1_WIN_BYTES
              : (static_cast<uint32_t>(3 * p.cin * 2 + 15) & ~15u) + PROD_GROUPS * 2 * TILE_M * 4u;
   o = (o + 15u) & ~15u;
   s.bar_off = o; o += (4 * MAX_STAGES + 2 * MAX_B_BLOCKS + 4) * 8 + 16;
@@ -222,31 +234,69 @@ __device__ __forceinline__ void produce_slab(const uint8_t* raw, uint8_t* slab, 
   }
 }
 
-// conv1 producer: stage the 5160-sample window of (clip-view, row block) in smem as fp16 with the
-// TTA view applied (coalesced scalar loads, circular index), then copy 16-byte chunks into the
-// swizzled slabs: row r = samples [40 r, 40 r + 80) of the window; slab 0 = first 64, slab 1 = last 16.
+// conv1 producer.  A tile is 128 output rows of one (clip, view group): row r needs samples
+// [40 r - 10, 40 r + 70) of the rolled clip, so the tile needs one contiguous window of
+// 40 (rows - 1) + 80 samples.  The window is fetched with source-aligned float4 loads (L % 4 == 0,
+// so a quad never straddles the np.roll wrap-around), one tile AHEAD of its use (registers), then
+// written to shared memory as fp16 at its rolled position, and finally copied as 16-byte chunks
+// into the swizzled slabs: slab 0 = first 64 samples of a row, slab 1 = last 16.
+struct Conv1Tile {
+  int ps_lo;        // first valid sample position of the window in rolled coordinates (>= 0)
+  int n;            // valid samples [ps_lo, ps_lo + n)
+  int win_off;      // ps_lo - p_start: where sample ps_lo lands in the window (10 for the first tile)
+  int src_al;       // 4-aligned source index of the first quad
+  int mis;          // source misalignment: quad element e of quad i is sample ps_lo + 4 i + e - mis
+  int rows;         // valid rows of the tile
+};
+
 struct Conv1Producer {
-  __device__ __forceinline__ static void stage_window(const GemmParams& p, int tile, int ptid, __half* s_win) {
-    const int rv = tile / p.tiles_per_group, jb = tile - rv * p.tiles_per_group;
-    const int b = rv / p.n_views, v = rv - b * p.n_views;
-    const int shift = p.vt.shift[v];
-    const float gain = p.vt.gain[v];
-    const float* x = p.wav + static_cast<size_t>(b) * L;
+  __device__ __forceinline__ static Conv1Tile describe(const GemmParams& p, int tile, const float** x) {
+    const int unit = tile / p.tiles_per_group, jb = tile - unit * p.tiles_per_group;
+    const int b = unit / p.vg.n_groups, g = unit - b * p.vg.n_groups;
+    const int sm = p.vg.shift[g];
+    *x = p.wav + static_cast<size_t>(b) * L;
+    Conv1Tile t;
+    t.rows = min(TILE_M, p.t_out - jb * TILE_M);
     const int p_start = CONV1_ROW_HOP * TILE_M * jb - 10;     // patch stack pads 10 samples on the left
-    int sm = shift % L; if (sm < 0) sm += L;
-    for (int i = ptid; i < CONV1_WIN; i += NUM_PROD_THREADS) {
-      const int ps = p_start + i;
-      float val = 0.0f;
-      if (ps >= 0 && ps < L) {
-        int src = ps - sm; if (src < 0) src += L;              // np.roll(x, shift)[ps]
-        val = __fmul_rn(gain, __ldg(&x[src]));
+    const int p_end = min(L, p_start + CONV1_ROW_HOP * (t.rows - 1) + CONV1_K);
+    t.ps_lo = max(p_start, 0);
+    t.n = p_end - t.ps_lo;
+    t.win_off = t.ps_lo - p_start;
+    int src = t.ps_lo - sm; if (src < 0) src += L;              // np.roll(x, shift)[ps] = x[(ps - shift) mod L]
+    t.src_al = src & ~3;
+    t.mis = src & 3;
+    return t;
+  }
+  __device__ __forceinline__ static void load(const Conv1Tile& t, const float* x, int ptid, float4 (&q)[CONV1_QUADS]) {
+    const int n_quads = (t.n + t.mis + 3) >> 2;
+#pragma unroll
+    for (int k = 0; k < CONV1_QUADS; ++k) {
+      const int i = ptid + k * NUM_PROD_THREADS;
+      if (i < n_quads) {
+        int s4 = t.src_al + 4 * i; if (s4 >= L) s4 -= L;
+        q[k] = __ldg(reinterpret_cast<const float4*>(x + s4));
       }
-      s_win[i] = __float2half_rn(val);
     }
   }
-  __device__ __forceinline__ static void fill_slabs(uint8_t* stage, int ptid, const __half* s_win) {
-    // 128 rows x 10 chunks (8 in slab 0, 2 in slab 1)
-    for (int task = ptid; task < TILE_M * 10; task += NUM_PROD_THREADS) {
+  __device__ __forceinline__ static void store(const Conv1Tile& t, int ptid, const float4 (&q)[CONV1_QUADS], __half* s_win) {
+    if (ptid < t.win_off) s_win[ptid] = __float2half_rn(0.0f);       // 'SAME' left pad of the patch stack
+    const int n_quads = (t.n + t.mis + 3) >> 2;
+#pragma unroll
+    for (int k = 0; k < CONV1_QUADS; ++k) {
+      const int i = ptid + k * NUM_PROD_THREADS;
+      if (i < n_quads) {
+        const int e0 = 4 * i - t.mis;                               // sample offset of element 0 from ps_lo
+        __half* dst = s_win + t.win_off + e0;
+        const float v[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (e0 + e >= 0 && e0 + e < t.n) dst[e] = __float2half_rn(v[e]);
+      }
+    }
+  }
+  __device__ __forceinline__ static void fill_slabs(uint8_t* stage, int ptid, const __half* s_win, int rows) {
+    // rows x 10 chunks (8 in slab 0, 2 in slab 1); rows beyond `rows` keep stale data and are never stored
+    for (int task = ptid; task < rows * 10; task += NUM_PROD_THREADS) {
       const int r = task / 10, ch = task - r * 10;
       const uint4 v = *reinterpret_cast<const uint4*>(s_win + CONV1_ROW_HOP * r + 8 * ch);
       uint8_t* slab = stage + (ch < 8 ? 0 : A_SLAB_BYTES);
@@ -259,8 +309,9 @@ struct Conv1Producer {
 // epilogue: 32 accumulator columns of one row -> +shift -> ReLU6 -> 32 fp16 = chunks ch0..ch0+3 of the
 // row's 128-byte line in the swizzled store box
 // ------------------------------------------------------------------------------------------------
+template <bool kGain>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const float* s_shift32, uint8_t* row_base,
-                                               int ch0, int sw) {
+                                               int ch0, int sw, float gain) {
   const __half2 six = __float2half2_rn(6.0f);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -268,8 +319,10 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const fl
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const float4 sh = *reinterpret_cast<const float4*>(s_shift32 + 8 * q + 4 * e);
-      const uint32_t a = pack_relu_f16x2(__uint_as_float(v[8 * q + 4 * e]) + sh.x, __uint_as_float(v[8 * q + 4 * e + 1]) + sh.y);
-      const uint32_t b = pack_relu_f16x2(__uint_as_float(v[8 * q + 4 * e + 2]) + sh.z, __uint_as_float(v[8 * q + 4 * e + 3]) + sh.w);
+      const float f0 = __uint_as_float(v[8 * q + 4 * e]), f1 = __uint_as_float(v[8 * q + 4 * e + 1]);
+      const float f2 = __uint_as_float(v[8 * q + 4 * e + 2]), f3 = __uint_as_float(v[8 * q + 4 * e + 3]);
+      const uint32_t a = kGain ? pack_relu_f16x2(fmaf(f0, gain, sh.x), fmaf(f1, gain, sh.y)) : pack_relu_f16x2(f0 + sh.x, f1 + sh.y);
+      const uint32_t b = kGain ? pack_relu_f16x2(fmaf(f2, gain, sh.z), fmaf(f3, gain, sh.w)) : pack_relu_f16x2(f2 + sh.z, f3 + sh.w);
       const __half2 ha = __hmin2(*reinterpret_cast<const __half2*>(&a), six);
       const __half2 hb = __hmin2(*reinterpret_cast<const __half2*>(&b), six);
       o[2 * e] = *reinterpret_cast<const uint32_t*>(&ha);
@@ -351,35 +404,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      int row0, rv = 0;                                          // first output row of this warp's box
+      int row0, rv0 = 0, m0 = 0, m1 = 1;                         // first output row of this warp's box; member views
       if (kConv1) {
-        rv = tile / p.tiles_per_group;
-        row0 = (tile - rv * p.tiles_per_group) * TILE_M + warp * 32;
+        const int unit = tile / p.tiles_per_group;
+        const int b = unit / p.vg.n_groups, g = unit - b * p.vg.n_groups;
+        rv0 = b * p.n_views;
+        m0 = p.vg.start[g]; m1 = p.vg.start[g + 1];
+        row0 = (tile - unit * p.tiles_per_group) * TILE_M + warp * 32;
+        if (row0 >= p.t_out) m1 = m0;                            // this warp's rows are all past the clip-view's end
       } else {
         row0 = tile * TILE_M + warp * 32;
       }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(acc * p.cout);
-      uint32_t va[32], vb[32];
-      tmem_ld32(taddr, va);
-      for (int c0 = 0; c0 < p.cout; c0 += 64) {
-        uint8_t* box = my_out + obuf * OUT_STAGE_BYTES;
-        uint8_t* row_base = box + lane * ROW_BYTES;
-        if (lane == 0) bulk_wait_group_read<1>();                // the store that last used this buffer has read it
-        __syncwarp();
-        tmem_ld_wait();
-        tmem_ld32(taddr + c0 + 32, vb);
-        epilogue_chunk(va, s_shift + c0, row_base, 0, lane & 7);
-        tmem_ld_wait();
-        if (c0 + 64 < p.cout) tmem_ld32(taddr + c0 + 64, va);
-        epilogue_chunk(vb, s_shift + c0 + 32, row_base, 4, lane & 7);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          if (kConv1) tma_store_3d(&p.tmap_out, c0, row0, rv, box);
-          else tma_store_2d(&p.tmap_out, c0, row0, box);
-          bulk_commit_group();
+      for (int mem = m0; mem < m1; ++mem) {
+        const float gain = kConv1 ? p.vg.gain[mem] : 1.0f;
+        const int rv = kConv1 ? rv0 + p.vg.view[mem] : 0;
+        uint32_t va[32], vb[32];
+        tmem_ld32(taddr, va);
+        for (int c0 = 0; c0 < p.cout; c0 += 64) {
+          uint8_t* box = my_out + obuf * OUT_STAGE_BYTES;
+          uint8_t* row_base = box + lane * ROW_BYTES;
+          if (lane == 0) bulk_wait_group_read<1>();              // the store that last used this buffer has read it
+          __syncwarp();
+          tmem_ld_wait();
+          tmem_ld32(taddr + c0 + 32, vb);
+          epilogue_chunk<kConv1>(va, s_shift + c0, row_base, 0, lane & 7, gain);
+          tmem_ld_wait();
+          if (c0 + 64 < p.cout) tmem_ld32(taddr + c0 + 64, va);
+          epilogue_chunk<kConv1>(vb, s_shift + c0 + 32, row_base, 4, lane & 7, gain);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (kConv1) tma_store_3d(&p.tmap_out, c0, row0, rv, box);
+            else tma_store_2d(&p.tmap_out, c0, row0, box);
+            bulk_commit_group();
+          }
+          obuf ^= 1;
         }
-        obuf ^= 1;
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[acc]);
@@ -483,16 +544,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     // =========================== A producers ===========================
     const int ptid = tid - PROD_WARP0 * 32;
     if constexpr (kConv1) {
-      int sa = 0; uint32_t pa = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        Conv1Producer::stage_window(p, tile, ptid, s_win);
+      int sa = 0; uint32_t pa = 0, buf = 0;
+      float4 q[CONV1_QUADS];
+      const float* x;
+      Conv1Tile cur{}, nxt{};
+      int tile = blockIdx.x;
+      if (tile < p.num_tiles) { cur = Conv1Producer::describe(p, tile, &x); Conv1Producer::load(cur, x, ptid, q); }
+      for (; tile < p.num_tiles; tile += gridDim.x) {
+        __half* win = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(s_win) + buf * CONV1_WIN_BYTES);
+        Conv1Producer::store(cur, ptid, q, win);
+        const int next = tile + gridDim.x;
+        if (next < p.num_tiles) {                                // next tile's loads fly while this one is filled
+          nxt = Conv1Producer::describe(p, next, &x);
+          Conv1Producer::load(nxt, x, ptid, q);
+        }
         asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");     // window complete
         mbar_wait(&a_empty[sa], pa ^ 1);
-        Conv1Producer::fill_slabs(a_base + sa * p.a_stage_bytes, ptid, s_win);
+        Conv1Producer::fill_slabs(a_base + sa * p.a_stage_bytes, ptid, win, cur.rows);
         fence_proxy_async_smem();
         mbar_arrive(&a_full[sa]);
         if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
-        asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");     // window free again
+        // no second barrier: the next tile writes the other window buffer, and this buffer is only
+        // rewritten after the next tile's bar.sync, which every thread reaches after this fill
+        buf ^= 1;
+        cur = nxt;
       }
     } else {
       const int grp = ptid / GROUP_THREADS, tg = ptid - grp * GROUP_THREADS;
@@ -678,6 +753,22 @@ int model_build_tc(kws_handle* h, Model& m, const std::vector<std::vector<float>
 int launch_forward_tc(kws_handle* h, Model& m, const float* wav, int B, const ViewTable& vt,
                       float* probs_mean, int32_t* argmax, cudaStream_t st, int dbg_layer, float* dbg_out) {
   const int V = vt.n;
+  ViewGroups vg{};
+  {
+    bool used[KWS_MAX_VIEWS] = {};
+    int mem = 0;
+    for (int v = 0; v < V; ++v) {
+      if (used[v]) continue;
+      int sm = vt.shift[v] % L; if (sm < 0) sm += L;
+      vg.shift[vg.n_groups] = sm;
+      vg.start[vg.n_groups] = mem;
+      for (int u = v; u < V; ++u) {
+        int su = vt.shift[u] % L; if (su < 0) su += L;
+        if (!used[u] && su == sm) { used[u] = true; vg.view[mem] = u; vg.gain[mem] = vt.gain[u]; ++mem; }
+      }
+      vg.start[++vg.n_groups] = mem;
+    }
+  }
   const int clips_per_chunk = std::max(1, h->max_rows / V);
   const size_t need = static_cast<size_t>(clips_per_chunk) * V * m.max_act_elems * sizeof(__half);
   if (h->act_bytes < need) {
@@ -695,12 +786,13 @@ int launch_forward_tc(kws_handle* h, Model& m, const float* wav, int B, const Vi
     __half* nxt = static_cast<__half*>(h->act[1]);
     {
       GemmParams p{};
-      p.wav = wav + static_cast<size_t>(b0) * L; p.vt = vt; p.n_views = V;
+      p.wav = wav + static_cast<size_t>(b0) * L; p.n_views = V;
+      p.vg = vg;
       p.w_img = reinterpret_cast<const uint8_t*>(m.tc_conv1);
       p.shift = m.bn_shift[0];
       p.cin = CONV1_K; p.cout = m.c0; p.t_out = m.t0; p.rows_out = rows * m.t0;
       p.tiles_per_group = (m.t0 + TILE_M - 1) / TILE_M;
-      p.num_tiles = rows * p.tiles_per_group;
+      p.num_tiles = nb * vg.n_groups * p.tiles_per_group;
       p.num_kb = 2; p.last_ksteps = 1;
       int rc = make_tensor_map(h, &p.tmap_out, cur, m.c0, m.t0, std::max(rows, 2), 32, true);   // 3-D: clip at t0
       if (rc) return rc;
