@@ -37,6 +37,29 @@ BYTES_AUGMENT = 192020                     # per clip
 ACT_BYTES_VIEW_FP16 = 286720 * 2 * 2       # 12 block outputs written + read once, fp16
 
 
+def block_bytes_per_view(arch=195):
+    """Algorithmic HBM bytes of each depthwise+pointwise block kernel per clip-view in the
+    block-materialised model of SURVEY.md 8(d) with fp16 activations: the block reads its input
+    activation [t_in, cin] once and writes its output [t_out, cout] once."""
+    from speech_recognition_b200.arch import ARCHS, layer_lengths
+    a = ARCHS[arch]
+    T = layer_lengths(arch)[1:]
+    out, cin = [], a["conv1"]
+    for i, (co, _) in enumerate(a["blocks"]):
+        out.append((T[i] * cin + T[i + 1] * co) * 2)
+        cin = co
+    return out
+
+
+def measured_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -251,6 +274,14 @@ def run_ours(args):
         blk_ms, blk_n = classes["dw_pw_blocks"]
         views_per_step = B * V
         blk_tflops = FLOP_BLOCKS * views_per_step * args.steps / (blk_ms / 1e3) / 1e12 if blk_ms > 0 else 0.0
+        # dominant kernel = the 11 block launches of each chunk; roofline on its algorithmic HBM bytes
+        bpv = block_bytes_per_view(195)
+        views_per_launch = min(args.max_rows // V * V, views_per_step)
+        alg_bytes_per_launch = sum(bpv) / len(bpv) * views_per_launch
+        blk_avg_launch_ms = blk_ms / max(blk_n, 1)
+        blk_gbs = alg_bytes_per_launch / (blk_avg_launch_ms / 1e3) / 1e9 if blk_ms > 0 else 0.0
+        tr = measured_traffic()
+        per_block = getattr(eng, "last_block_ms", None)
         per_class = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
                      for k, v in classes.items() if v[1]}
         aug_ms = classes["augment"][0] / args.steps
@@ -265,12 +296,16 @@ def run_ours(args):
                        "l2_policy": "inputs larger than L2 (batch x 64 KB = %.0f MB)" % (B * 64e3 / 1e6),
                        "precision": args.precision, "max_rows": args.max_rows,
                        "parallelism": f"dp{world} (clip shards, 1 all-gather of probabilities per step)"},
-            "roofline": {"kernel": "tc_gemm_kernel (depthwise producer + tcgen05 pointwise GEMM + BN/ReLU6), "
-                                   "11 launches per chunk" if args.precision == "tc" else "gemm_f32_kernel",
-                         "bound": "tensor", "achieved": blk_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": blk_tflops / peaks["tflops"], "peak_source": peaks["source"] + " (sustained bf16)",
-                         "traffic": None,
-                         "share_of_step": blk_ms / ms if ms else None},
+            "roofline": {"kernel": "tc_gemm_kernel<1|2> (TMA-fed depthwise producer + tcgen05 pointwise GEMM + BN/ReLU6 "
+                                   "+ TMA store), 11 launches per chunk" if args.precision == "tc" else "gemm_f32_kernel",
+                         "bound": "hbm", "achieved": blk_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": blk_gbs / peaks["hbm_gbs"], "peak_source": peaks["source"] + " (copy bandwidth)",
+                         "algorithmic_bytes_per_launch": alg_bytes_per_launch,
+                         "avg_launch_ms": blk_avg_launch_ms, "clip_views_per_launch": views_per_launch,
+                         "traffic": tr["bytes_per_launch"] if tr else None,
+                         "traffic_source": tr["source"] if tr else None,
+                         "share_of_step": blk_ms / ms if ms else None,
+                         "tensor_tflops": blk_tflops, "tensor_frac": blk_tflops / peaks["tflops"]},
             "secondary_rooflines": {
                 "augment_hbm_gbs": BYTES_AUGMENT * B / (aug_ms / 1e3) / 1e9 if aug_ms else None,
                 "augment_hbm_frac": (BYTES_AUGMENT * B / (aug_ms / 1e3) / 1e9) / peaks["hbm_gbs"] if aug_ms else None,
@@ -279,6 +314,7 @@ def run_ours(args):
                 * args.steps / (ms / 1e3) / 1e9 / peaks["hbm_gbs"],
             },
             "kernel_classes": per_class,
+            "block_ms_per_step": [round(b[0] / args.steps, 4) for b in per_block] if per_block else None,
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "kws_pipeline_host (ctypes, pinned host buffers)"},
             "gpu_launches": launches,

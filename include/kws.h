@@ -79,7 +79,8 @@ int64_t kws_launch_count(const kws_t* h);
 /* Per-kernel-class device timing for roofline reports: when enabled every launch is bracketed
  * by CUDA events on its stream; kws_timing_read() synchronises, sums the elapsed milliseconds
  * and launch counts per class and resets.  Classes: 0 augment, 1 DFT/STFT GEMM, 2 mel+DCT,
- * 3 slice_conv1, 4 depthwise+pointwise blocks, 5 head, 6 other (n_classes >= 7). */
+ * 3 slice_conv1, 4 depthwise+pointwise blocks, 5 head, 6 other (n_classes >= 7); with n_classes >= 18,
+ * slots 7..17 additionally hold the 11 blocks individually (tensor-core tier). */
 int kws_timing_enable(kws_t* h, int on);
 int kws_timing_read(kws_t* h, double* ms_per_class, int64_t* count_per_class, int n_classes);
 

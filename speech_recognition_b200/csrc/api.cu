@@ -166,7 +166,12 @@ int kws_timing_read(kws_t* h, double* ms_per_class, int64_t* count_per_class, in
     KWS_CUDA(h, cudaEventSynchronize(t.e1));
     float ms = 0.f;
     KWS_CUDA(h, cudaEventElapsedTime(&ms, t.e0, t.e1));
-    ms_per_class[t.cls] += ms; count_per_class[t.cls]++;
+    int cls = t.cls;
+    if (cls >= KC_BLOCK0) {                                    // per-block slot when the caller asked for them
+      if (cls < n_classes) { ms_per_class[cls] += ms; count_per_class[cls]++; }
+      cls = KC_BLOCKS;
+    }
+    ms_per_class[cls] += ms; count_per_class[cls]++;
     h->event_pool.push_back(t.e0); h->event_pool.push_back(t.e1);
   }
   h->timed.clear();

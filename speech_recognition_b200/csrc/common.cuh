@@ -127,7 +127,9 @@ int ensure_bytes(kws_handle* h, void** p, size_t* cur, size_t need, bool pinned 
   } while (0)
 
 // kernel classes for kws_timing_read
-enum { KC_AUGMENT = 0, KC_DFT = 1, KC_MELDCT = 2, KC_CONV1 = 3, KC_BLOCKS = 4, KC_HEAD = 5, KC_OTHER = 6, KC_COUNT = 7 };
+// classes 7..17 = the 11 depthwise+pointwise blocks individually (also summed into KC_BLOCKS)
+enum { KC_AUGMENT = 0, KC_DFT = 1, KC_MELDCT = 2, KC_CONV1 = 3, KC_BLOCKS = 4, KC_HEAD = 5, KC_OTHER = 6, KC_COUNT = 7,
+       KC_BLOCK0 = 7, KC_COUNT_EXT = 18 };
 void timer_begin(kws_handle* h, int cls, cudaStream_t st);
 void timer_end(kws_handle* h, cudaStream_t st);
 #define KWS_T0(h, cls, st) do { if ((h)->timing) kws::timer_begin((h), (cls), (st)); } while (0)

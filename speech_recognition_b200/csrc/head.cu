@@ -75,7 +75,7 @@ head_kernel(const TAct* __restrict__ act, int C, int n_views, int n_clips, const
       float p[HEAD_T];
 #pragma unroll
       for (int j = 0; j < HEAD_T; ++j) p[j] = 0.0f;
-#pragma unroll 4
+#pragma unroll 16                                        // 16 activation loads in flight per lane (latency-bound otherwise)
       for (int i = lane; i < n; i += 32) {
         const float xv = to_float(x[i]);
         const float* wr = w1 + i * HEAD_T;

@@ -24,6 +24,7 @@
 // [0,6] so the range is safe), accumulation is fp32 in TMEM.  The BatchNorm scale is folded into
 // the fp16 weights at load time, the shift stays fp32 in the epilogue.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include <cuda.h>
@@ -73,6 +74,7 @@ struct alignas(64) GemmParams {
   CUtensorMap tmap_in;      // dw_pw: previous activation [rows_in, cin] fp16, box [box_rows, 64]
   CUtensorMap tmap_out;     // output activation, box [32 rows, 64 ch], 128-byte swizzle; dw_pw: 2-D
                             // [rows_out, cout]; conv1: 3-D [clip-views, t_out, cout] (rows clipped per view)
+  CUtensorMap tmap_tail;    // dw_pw with ncta % 64 == 32: box [32 rows, 32 ch], no swizzle, for the last 32 columns
   // conv1 A side
   const float* wav;         // waveforms [B, 16000] fp32
   ViewGroups vg;            // TTA views grouped by shift: one staged window + one MMA per (clip, group),
@@ -83,6 +85,9 @@ struct alignas(64) GemmParams {
   const uint8_t* w_img;
   // epilogue
   const float* shift;       // beta - mean * scale (the scale lives in the weights)
+  int block_index;          // host-side only: which block this launch is (timing class)
+  const __half* out_act;    // host-side only: the output activation (for the tail tensor map)
+  long long out_rows;
   // shapes
   int cin, cout, stride, pad_left, t_in, t_out;
   int rows_out;             // valid output rows
@@ -91,14 +96,17 @@ struct alignas(64) GemmParams {
   int num_kb;               // K slabs
   int last_ksteps;          // K=16 steps in the last slab (4, or 1 for conv1)
   int a_stages, b_stages, acc_stages, b_resident, raw_stages;
-  int n_inst, n_halves;     // cout = n_inst * n_halves, n_inst <= 256
+  int n_split, ncta;        // the cout columns are split over n_split adjacent CTAs, ncta = cout / n_split each:
+                            // CTA c works on columns [(c % n_split) * ncta, +ncta) of tiles c / n_split, + grid / n_split, ...
+                            // so that its slice of the weights stays resident and two accumulators fit in TMEM
+  int n_inst, n_halves;     // ncta = n_inst * n_halves, n_inst <= 256
+  int out_bufs;             // store boxes per epilogue warp (2, or 1 when shared memory is short)
   int a_stage_bytes;        // dw_pw: 16 KB; conv1: 32 KB (both slabs of a tile)
   int raw_stage_bytes, box_rows, n_boxes;
   unsigned long long t_out_magic;   // ceil(2^40 / t_out)
 };
 
 constexpr int OUT_STAGE_BYTES = 32 * ROW_BYTES;                 // one warp's [32 rows x 64 ch] store box
-constexpr int OUT_BYTES = NUM_EPI_WARPS * 2 * OUT_STAGE_BYTES;  // double-buffered per epilogue warp (32 KB)
 
 struct SmemLayout {
   uint32_t a_off, b_off, out_off, raw_off, aux_off, bar_off, total;
@@ -109,12 +117,12 @@ __host__ __device__ inline SmemLayout smem_layout(const GemmParams& p, bool conv
   uint32_t o = 0;
   s.a_off = o; o += static_cast<uint32_t>(p.a_stages) * p.a_stage_bytes;
   s.b_off = o; o += static_cast<uint32_t>(p.b_stages) * p.n_inst * ROW_BYTES;
-  s.out_off = o; o += OUT_BYTES;
+  s.out_off = o; o += static_cast<uint32_t>(NUM_EPI_WARPS * p.out_bufs * OUT_STAGE_BYTES);
   s.raw_off = o; o += static_cast<uint32_t>(p.raw_stages) * p.raw_stage_bytes;
   s.aux_off = o;
   // aux: shift[cout] fp32, then (dw_pw) taps [3*cin] fp16 + row metadata [2 groups][2 parities][128] u32
   //      or (conv1) the staged fp16 waveform window
-  o += static_cast<uint32_t>(p.cout) * 4u;
+  o += static_cast<uint32_t>(p.ncta) * 4u;
   o += conv1 ? 2u * CONV1_WIN_BYTES
              : (static_cast<uint32_t>(3 * p.cin * 2 + 15) & ~15u) + PROD_GROUPS * 2 * TILE_M * 4u;
   o = (o + 15u) & ~15u;
@@ -347,9 +355,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   uint8_t* raw_base = smem + lay.raw_off;
   uint8_t* out_base = smem + lay.out_off;
   float* s_shift = reinterpret_cast<float*>(smem + lay.aux_off);
-  __half* s_dwh = reinterpret_cast<__half*>(s_shift + p.cout);                       // dw_pw
+  __half* s_dwh = reinterpret_cast<__half*>(s_shift + p.ncta);                       // dw_pw
   uint32_t* s_meta = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(s_dwh) + ((3 * p.cin * 2 + 15) & ~15));
-  __half* s_win = reinterpret_cast<__half*>(s_shift + p.cout);                       // conv1
+  __half* s_win = reinterpret_cast<__half*>(s_shift + p.ncta);                       // conv1
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_off);
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + MAX_STAGES;
@@ -362,9 +370,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int col0 = (static_cast<int>(blockIdx.x) % p.n_split) * p.ncta;      // this CTA's output columns
+  const int tile0 = static_cast<int>(blockIdx.x) / p.n_split;
+  const int tstride = static_cast<int>(gridDim.x) / p.n_split;
 
   // ---- one-time setup ----
-  for (int i = tid; i < p.cout; i += TC_THREADS) s_shift[i] = p.shift[i];
+  for (int i = tid; i < p.ncta; i += TC_THREADS) s_shift[i] = p.shift[col0 + i];
   if (!kConv1)
     for (int i = tid; i < 3 * p.cin; i += TC_THREADS) s_dwh[i] = p.dw_h[i];
   if (warp == MMA_WARP) {
@@ -398,10 +409,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     // and one lane hands the box to the TMA store engine: full 128-byte lines leave the SM, rows
     // beyond the tensor (or beyond the clip-view for conv1) are clipped by the tensor map.
     int acc = 0; uint32_t acc_phase = 0;
-    uint8_t* my_out = out_base + warp * 2 * OUT_STAGE_BYTES;
+    uint8_t* my_out = out_base + warp * p.out_bufs * OUT_STAGE_BYTES;
     int obuf = 0;
     if (lane == 0) tma_prefetch_desc(&p.tmap_out);
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < p.num_tiles; tile += tstride) {
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       int row0, rv0 = 0, m0 = 0, m1 = 1;                         // first output row of this warp's box; member views
@@ -415,31 +426,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       } else {
         row0 = tile * TILE_M + warp * 32;
       }
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(acc * p.cout);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(acc * p.ncta);
       for (int mem = m0; mem < m1; ++mem) {
         const float gain = kConv1 ? p.vg.gain[mem] : 1.0f;
         const int rv = kConv1 ? rv0 + p.vg.view[mem] : 0;
         uint32_t va[32], vb[32];
         tmem_ld32(taddr, va);
-        for (int c0 = 0; c0 < p.cout; c0 += 64) {
+        for (int c0 = 0; c0 < p.ncta; c0 += 64) {
+          const bool tail = p.ncta - c0 < 64;                    // last 32 columns of a 160- or 96-column slice
           uint8_t* box = my_out + obuf * OUT_STAGE_BYTES;
-          uint8_t* row_base = box + lane * ROW_BYTES;
-          if (lane == 0) bulk_wait_group_read<1>();              // the store that last used this buffer has read it
+          if (lane == 0) {                                       // the store that last used this buffer has read it
+            if (p.out_bufs == 2) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
+          }
           __syncwarp();
           tmem_ld_wait();
-          tmem_ld32(taddr + c0 + 32, vb);
-          epilogue_chunk<kConv1>(va, s_shift + c0, row_base, 0, lane & 7, gain);
-          tmem_ld_wait();
-          if (c0 + 64 < p.cout) tmem_ld32(taddr + c0 + 64, va);
-          epilogue_chunk<kConv1>(vb, s_shift + c0 + 32, row_base, 4, lane & 7, gain);
+          if (!tail) {
+            uint8_t* row_base = box + lane * ROW_BYTES;
+            tmem_ld32(taddr + c0 + 32, vb);
+            epilogue_chunk<kConv1>(va, s_shift + c0, row_base, 0, lane & 7, gain);
+            tmem_ld_wait();
+            if (c0 + 64 < p.ncta) tmem_ld32(taddr + c0 + 64, va);
+            epilogue_chunk<kConv1>(vb, s_shift + c0 + 32, row_base, 4, lane & 7, gain);
+          } else {
+            epilogue_chunk<kConv1>(va, s_shift + c0, box + lane * (ROW_BYTES / 2), 0, 0, gain);   // dense 64-byte rows
+          }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
             if (kConv1) tma_store_3d(&p.tmap_out, c0, row0, rv, box);
-            else tma_store_2d(&p.tmap_out, c0, row0, box);
+            else if (tail) tma_store_2d(&p.tmap_tail, col0 + c0, row0, box);
+            else tma_store_2d(&p.tmap_out, col0 + c0, row0, box);
             bulk_commit_group();
           }
-          obuf ^= 1;
+          obuf = (obuf + 1) & (p.out_bufs - 1);
         }
       }
       tc_fence_before();
@@ -452,10 +471,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16(TILE_M, p.n_inst, /*fp16*/ 0);
       int sa = 0; uint32_t pa = 0; int sb = 0; uint32_t pb = 0; int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < p.num_tiles; tile += tstride) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + static_cast<uint32_t>(acc * p.cout);
+        const uint32_t d0 = tmem_base + static_cast<uint32_t>(acc * p.ncta);
         if (kConv1) mbar_wait(&a_full[sa], pa);                  // one stage = both slabs of the tile
         for (int kb = 0; kb < p.num_kb; ++kb) {
           uint32_t a_addr;
@@ -503,7 +522,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     if (lane == 0) {
       auto load_block = [&](int j, int slot, uint64_t* bar) {
         mbar_arrive_expect_tx(bar, b_block_bytes);
-        const uint8_t* src = p.w_img + static_cast<size_t>(j) * b_block_bytes;
+        // image = [K slab][cout rows x 128 B]; block j = (K slab j / n_halves, rows col0 + (j % n_halves) * n_inst ...)
+        const uint8_t* src = p.w_img + (static_cast<size_t>(j / p.n_halves) * p.cout + col0 + (j % p.n_halves) * p.n_inst) * ROW_BYTES;
         uint8_t* dst = b_base + slot * b_block_bytes;
         for (uint32_t o = 0; o < b_block_bytes; o += 16384)
           bulk_g2s(dst + o, src + o, min(16384u, b_block_bytes - o), bar);
@@ -512,7 +532,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         for (int j = 0; j < blocks_per_tile; ++j) load_block(j, j, &b_full[j]);
       } else {
         int sb = 0; uint32_t pb = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < p.num_tiles; tile += tstride) {
           for (int j = 0; j < blocks_per_tile; ++j) {
             mbar_wait(&b_empty[sb], pb ^ 1);
             load_block(j, sb, &b_full[sb]);
@@ -525,7 +545,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     // =========================== raw activation loader (TMA) ===========================
     if (!kConv1 && lane == 0) {
       int rs = 0; uint32_t pr = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < p.num_tiles; tile += tstride) {
         const int m0 = tile * TILE_M;
         const int v0 = div_t_out(p, m0), t0 = m0 - v0 * p.t_out;
         const int lo = v0 * p.t_in + t0 * kStride - p.pad_left;
@@ -548,12 +568,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       float4 q[CONV1_QUADS];
       const float* x;
       Conv1Tile cur{}, nxt{};
-      int tile = blockIdx.x;
+      int tile = tile0;
       if (tile < p.num_tiles) { cur = Conv1Producer::describe(p, tile, &x); Conv1Producer::load(cur, x, ptid, q); }
-      for (; tile < p.num_tiles; tile += gridDim.x) {
+      for (; tile < p.num_tiles; tile += tstride) {
         __half* win = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(s_win) + buf * CONV1_WIN_BYTES);
         Conv1Producer::store(cur, ptid, q, win);
-        const int next = tile + gridDim.x;
+        const int next = tile + tstride;
         if (next < p.num_tiles) {                                // next tile's loads fly while this one is filled
           nxt = Conv1Producer::describe(p, next, &x);
           Conv1Producer::load(nxt, x, ptid, q);
@@ -573,7 +593,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       const int grp = ptid / GROUP_THREADS, tg = ptid - grp * GROUP_THREADS;
       uint32_t* meta_g = s_meta + grp * 2 * TILE_M;
       int n_base = 0, par = 0;                                   // n = running slab number of this CTA
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < p.num_tiles; tile += tstride) {
         uint32_t* meta = meta_g + par * TILE_M;
         meta[tg] = row_meta(p, kStride, tile, tg);
         if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(GROUP_THREADS) : "memory");
@@ -642,14 +662,14 @@ EncodeTiledFn encode_tiled_fn() {
 
 // fp16 channels-last activation [d2][d1][c] (d2 = 1 for a plain [rows, c] matrix); box = [1][box_rows][64 ch]
 int make_tensor_map(kws_handle* h, CUtensorMap* tm, const __half* act, int c, long long d1, long long d2,
-                    int box_rows, bool swizzle128) {
+                    int box_rows, bool swizzle128, int box_ch = SLAB_K) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return fail(h, KWS_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint32_t rank = d2 > 1 ? 3 : 2;
   const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(d1), static_cast<cuuint64_t>(d2)};
   const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(c) * sizeof(__half),
                                  static_cast<cuuint64_t>(c) * sizeof(__half) * static_cast<cuuint64_t>(d1)};
-  const cuuint32_t box[3] = {static_cast<cuuint32_t>(SLAB_K), static_cast<cuuint32_t>(box_rows), 1};
+  const cuuint32_t box[3] = {static_cast<cuuint32_t>(box_ch), static_cast<cuuint32_t>(box_rows), 1};
   const cuuint32_t estride[3] = {1, 1, 1};
   const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<__half*>(act), gdim, gstride, box, estride,
                         CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -662,37 +682,77 @@ int make_tensor_map(kws_handle* h, CUtensorMap* tm, const __half* act, int c, lo
 template <int MODE>
 int launch_tc_gemm(kws_handle* h, GemmParams& p, cudaStream_t st) {
   const bool conv1 = MODE == 0;
-  // split cout into <= 256-wide instructions
-  p.n_halves = p.cout > 256 ? 2 : 1;
-  p.n_inst = p.cout / p.n_halves;
-  if (p.n_inst % 16 || p.n_inst > 256 || p.cout > TMEM_COLS || p.cout % 32)
-    return fail(h, KWS_EUNSUPPORTED, "unsupported channel count for the tensor-core path");
-  p.acc_stages = std::min(2, TMEM_COLS / p.cout);
+  if (p.cout % 32 || p.cout > 4 * 256) return fail(h, KWS_EUNSUPPORTED, "unsupported channel count for the tensor-core path");
+  auto set_split = [&](int ns) {
+    p.n_split = ns; p.ncta = p.cout / ns;
+    p.n_halves = p.ncta > 256 ? 2 : 1;                          // split ncta into <= 256-wide instructions
+    p.n_inst = p.ncta / p.n_halves;
+    p.acc_stages = std::min(2, TMEM_COLS / p.ncta);
+    return p.cout % ns == 0 && p.ncta % 32 == 0 && p.n_inst % 16 == 0 && p.n_inst <= 256 && p.ncta <= TMEM_COLS;
+  };
   p.a_stage_bytes = conv1 ? 2 * A_SLAB_BYTES : A_SLAB_BYTES;
-  const int blocks = p.num_kb * p.n_halves;
+  p.out_bufs = 2;
   auto fits = [&](int a, int b, int r) {
     p.a_stages = a; p.b_stages = b; p.raw_stages = r;
     return static_cast<int>(smem_layout(p, conv1).total) <= SMEM_LIMIT;
   };
   bool chosen = false;
   if (conv1) {
+    if (!set_split(1)) return fail(h, KWS_EUNSUPPORTED, "unsupported conv1d_1 width");
+    const int blocks = p.num_kb * p.n_halves;
     p.b_resident = 1;
     chosen = fits(3, blocks, 0) || fits(2, blocks, 0);
   } else {
     // The two producer groups work on alternate slabs, so the A and raw rings need EVEN depths: with
     // slot = n % depth every slot then belongs to one group, and no thread ever waits on an mbarrier
     // more than one phase ahead of it (a group that skipped a slot's previous use would otherwise
-    // see a stale parity).  Preference: weights resident, deep A ring, then deep raw ring.
-    const int b_block = p.n_inst * ROW_BYTES;
-    const int b_stream = std::max(2, std::min(4, 65536 / b_block));
+    // see a stale parity).
+    // Wide layers (cout > 256) cannot double-buffer their accumulator in TMEM nor keep their weights
+    // in shared memory, which serialises MMA and epilogue and re-streams up to 512 KB of weights per
+    // tile from L2.  They are split column-wise over 2-4 adjacent CTAs instead: each CTA keeps its
+    // slice of the weights resident for the whole launch and owns two accumulator stages; the A
+    // operand of a row tile is then produced once per slice (its raw rows come from L2 after the
+    // first CTA touched them).  Preference: smallest split with resident weights, deep A ring, deep raw ring.
     const int r_min = MODE == 1 ? 4 : 2;
-    for (int a = 4; a >= 2 && !chosen; a -= 2)
-      for (int res = 1; res >= 0 && !chosen; --res) {
-        if (res && blocks > MAX_B_BLOCKS) continue;
-        for (int bs = res ? blocks : b_stream; bs >= (res ? blocks : 2) && !chosen; --bs)
-          for (int r = 6; r >= r_min && !chosen; r -= 2)
-            if (fits(a, bs, r)) { p.b_resident = res; chosen = true; }
+    auto search = [&](int ns_lo, int ns_hi, bool resident_only, int ob_lo) {
+      for (int ns = ns_lo; ns <= ns_hi && !chosen; ++ns) {
+        if (!set_split(ns)) continue;
+        const int blocks = p.num_kb * p.n_halves;
+        const int b_block = p.n_inst * ROW_BYTES;
+        const int b_stream = std::max(2, std::min(4, 65536 / b_block));
+        if (ob_lo == 2) {                                        // narrow layers: deep A ring first
+          p.out_bufs = 2;
+          for (int a = 4; a >= 2 && !chosen; a -= 2)
+            for (int res = 1; res >= (resident_only ? 1 : 0) && !chosen; --res) {
+              if (res && blocks > MAX_B_BLOCKS) continue;
+              for (int bs = res ? blocks : b_stream; bs >= (res ? blocks : 2) && !chosen; --bs)
+                for (int r = 6; r >= r_min && !chosen; r -= 2)
+                  if (fits(a, bs, r)) { p.b_resident = res; chosen = true; }
+            }
+        } else {                                                 // split layers: deep raw ring (HBM/L2 latency) first
+          for (int res = 1; res >= (resident_only ? 1 : 0) && !chosen; --res) {
+            if (res && blocks > MAX_B_BLOCKS) continue;
+            for (int r = 6; r >= 2 && !chosen; r -= 2)
+              for (int ob = 2; ob >= 1 && !chosen; --ob) {
+                p.out_bufs = ob;
+                for (int a = 4; a >= 2 && !chosen; a -= 2)
+                  for (int bs = res ? blocks : b_stream; bs >= (res ? blocks : 2) && !chosen; --bs)
+                    if (fits(a, bs, r)) { p.b_resident = res; chosen = true; }
+              }
+          }
+        }
       }
+    };
+    // Measured (profiles/): the 2-way split pays for the stride-1 wide layers (320->320, 384->384, 512->512); the
+    // stride-2 ones have double-size raw stages, lose their TMA prefetch depth to the resident weights and get
+    // slower, and 3/4-way splits re-read the raw rows more than they save in weight traffic.
+    static const int max_split = [] { const char* e = getenv("KWS_MAX_SPLIT"); return e ? atoi(e) : 2; }();   // A/B aid
+    if (p.cout <= 256 || max_split < 2 || MODE != 1) {
+      search(1, 1, false, 2);                                    // weights resident when they fit, else streamed
+    } else {
+      search(2, max_split, true, 1);
+      if (!chosen) search(2, max_split, false, 1);
+    }
   }
   if (!chosen) return fail(h, KWS_EUNSUPPORTED, "layer does not fit in shared memory");
   const SmemLayout lay = smem_layout(p, conv1);
@@ -701,16 +761,21 @@ int launch_tc_gemm(kws_handle* h, GemmParams& p, cudaStream_t st) {
     KWS_CUDA(h, cudaFuncSetAttribute(tc_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_set[MODE] = true;
   }
-  const int grid = std::min(p.num_tiles, h->num_sms);
+  const int grid = std::min(p.num_tiles, h->num_sms / p.n_split) * p.n_split;
   if (grid <= 0) return KWS_OK;
-  KWS_T0(h, MODE == 0 ? KC_CONV1 : KC_BLOCKS, st);
+  if (!conv1 && p.ncta % 64) {                                   // 32-column tail boxes of this launch's output
+    const int rc = make_tensor_map(h, &p.tmap_tail, p.out_act, p.cout, p.out_rows, 1, 32, false, 32);
+    if (rc) return rc;
+  }
+  KWS_T0(h, MODE == 0 ? KC_CONV1 : KC_BLOCK0 + p.block_index, st);
   tc_gemm_kernel<MODE><<<grid, TC_THREADS, lay.total, st>>>(p);
   KWS_T1(h, st);
   if (debug_sync() && cudaDeviceSynchronize() != cudaSuccess)
     return fail(h, KWS_ECUDA, "tc_gemm_kernel<" + std::to_string(MODE) + "> cin " + std::to_string(p.cin) + " cout " +
                                   std::to_string(p.cout) + " rows_out " + std::to_string(p.rows_out) + " stages a/b/raw " +
                                   std::to_string(p.a_stages) + "/" + std::to_string(p.b_stages) + "/" +
-                                  std::to_string(p.raw_stages) + " resident " + std::to_string(p.b_resident) + ": " +
+                                  std::to_string(p.raw_stages) + " resident " + std::to_string(p.b_resident) + " split " +
+                                  std::to_string(p.n_split) + " out_bufs " + std::to_string(p.out_bufs) + ": " +
                                   cudaGetErrorString(cudaGetLastError()));
   KWS_LAUNCH_CHECK(h);
   return KWS_OK;
@@ -824,6 +889,7 @@ int launch_forward_tc(kws_handle* h, Model& m, const float* wav, int B, const Vi
       if (rc) return rc;
       rc = make_tensor_map(h, &p.tmap_out, nxt, d.cout, static_cast<long long>(rows) * d.t_out, 1, 32, true);
       if (rc) return rc;
+      p.block_index = i; p.out_act = nxt; p.out_rows = static_cast<long long>(rows) * d.t_out;
       rc = d.stride == 1 ? launch_tc_gemm<1>(h, p, st) : launch_tc_gemm<2>(h, p, st);
       if (rc) return rc;
       std::swap(cur, nxt);

@@ -79,10 +79,12 @@ class Engine:
 
     def timing_read(self):
         """{class: (total_ms, launches)} since the last read (synchronises)."""
-        ms = (C.c_double * 7)()
-        cnt = (C.c_int64 * 7)()
-        self._check(self.lib.kws_timing_read(self.h, ms, cnt, 7))
-        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
+        ms = (C.c_double * 18)()
+        cnt = (C.c_int64 * 18)()
+        self._check(self.lib.kws_timing_read(self.h, ms, cnt, 18))
+        out = {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
+        self.last_block_ms = [(float(ms[7 + i]), int(cnt[7 + i])) for i in range(11)]   # per dw+pw block (tc tier)
+        return out
 
     # -- stage 1a --
     def set_noise_bank(self, bank_t, file_offsets):

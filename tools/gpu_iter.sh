@@ -9,7 +9,7 @@ import json
 try:
     d=json.load(open("gpurun_out/bench_iter.json"))
     print("value",round(d["value"]),"ms/step",round(d["ms_per_step"],3),"e2e",round(d["e2e"]["value"]))
-    print({k:round(v["ms_per_step"],3) for k,v in d["kernel_classes"].items()})
+    print({k:round(v["ms_per_step"],3) for k,v in d["kernel_classes"].items()}); print("blocks",d.get("block_ms_per_step"))
     print("roofline",d["roofline"]["achieved"],d["roofline"]["frac"])
 except Exception as e:
     print("bench failed",e); print(open("gpurun_out/bench_iter.err").read()[-2000:])
