@@ -38,16 +38,24 @@ using namespace tc;
 
 namespace {
 
-constexpr int NUM_EPI_WARPS = 4;
-constexpr int NUM_PROD_WARPS = 8;
-constexpr int NUM_PROD_THREADS = NUM_PROD_WARPS * 32;           // 256
+// Warp roles depend on the layer type: the dw_pw blocks are fed by 8 depthwise producer warps and
+// drained by 4 epilogue warps; conv1d_1 is bound by its epilogue (one pass per TTA view of a
+// group over a K = 80 GEMM), so it gets 8 epilogue warps (two per TMEM lane quarter, alternating
+// 64-column chunks), 6 producer warps and no raw-loader warp.
+template <int MODE> struct Roles {
+  static constexpr int EPI_WARPS = MODE == 0 ? 8 : 4;
+  static constexpr int MMA_WARP = EPI_WARPS;
+  static constexpr int LOAD_WARP = EPI_WARPS + 1;
+  static constexpr int RAW_WARP = MODE == 0 ? -1 : EPI_WARPS + 2;
+  static constexpr int PROD_WARP0 = MODE == 0 ? EPI_WARPS + 2 : EPI_WARPS + 3;
+  static constexpr int PROD_WARPS = MODE == 0 ? 6 : 8;
+  static constexpr int PROD_THREADS = PROD_WARPS * 32;           // 192 / 256
+  static constexpr int THREADS = 32 * (PROD_WARP0 + PROD_WARPS); // 512 / 480
+};
+constexpr int NUM_PROD_THREADS = Roles<1>::PROD_THREADS;         // dw_pw: 256
+constexpr int CONV1_PROD_THREADS = Roles<0>::PROD_THREADS;       // conv1: 192
 constexpr int PROD_GROUPS = 2;                                   // dw_pw: groups on alternate slabs
 constexpr int GROUP_THREADS = NUM_PROD_THREADS / PROD_GROUPS;    // 128
-constexpr int MMA_WARP = NUM_EPI_WARPS;                          // 4
-constexpr int LOAD_WARP = NUM_EPI_WARPS + 1;                     // 5
-constexpr int RAW_WARP = NUM_EPI_WARPS + 2;                      // 6
-constexpr int PROD_WARP0 = NUM_EPI_WARPS + 3;                    // 7
-constexpr int TC_THREADS = 32 * (PROD_WARP0 + NUM_PROD_WARPS);   // 480
 constexpr int MAX_STAGES = 8;                                    // A / raw rings
 constexpr int MAX_B_BLOCKS = 16;                                 // B ring (K slabs x N halves)
 constexpr int TMEM_COLS = 512;
@@ -57,7 +65,7 @@ constexpr int CONV1_K = 80;                                      // samples per 
 constexpr int CONV1_ROW_HOP = 40;
 constexpr int CONV1_WIN = CONV1_ROW_HOP * (TILE_M - 1) + CONV1_K;   // 5160 staged samples per tile
 constexpr uint32_t CONV1_WIN_BYTES = ((CONV1_WIN + 8) * 2 + 15) & ~15;   // one fp16 window buffer
-constexpr int CONV1_QUADS = 6;                                   // float4 loads per producer thread and tile
+constexpr int CONV1_QUADS = 7;                                   // float4 loads per producer thread and tile (1291 quads / 192 threads)
 
 
 // TTA views that share a roll shift differ only by the gain, and conv1d_1 is linear and bias-free
@@ -117,7 +125,7 @@ __host__ __device__ inline SmemLayout smem_layout(const GemmParams& p, bool conv
   uint32_t o = 0;
   s.a_off = o; o += static_cast<uint32_t>(p.a_stages) * p.a_stage_bytes;
   s.b_off = o; o += static_cast<uint32_t>(p.b_stages) * p.n_inst * ROW_BYTES;
-  s.out_off = o; o += static_cast<uint32_t>(NUM_EPI_WARPS * p.out_bufs * OUT_STAGE_BYTES);
+  s.out_off = o; o += static_cast<uint32_t>((conv1 ? Roles<0>::EPI_WARPS : Roles<1>::EPI_WARPS) * p.out_bufs * OUT_STAGE_BYTES);
   s.raw_off = o; o += static_cast<uint32_t>(p.raw_stages) * p.raw_stage_bytes;
   s.aux_off = o;
   // aux: shift[cout] fp32, then (dw_pw) taps [3*cin] fp16 + row metadata [2 groups][2 parities][128] u32
@@ -279,7 +287,7 @@ struct Conv1Producer {
     const int n_quads = (t.n + t.mis + 3) >> 2;
 #pragma unroll
     for (int k = 0; k < CONV1_QUADS; ++k) {
-      const int i = ptid + k * NUM_PROD_THREADS;
+      const int i = ptid + k * CONV1_PROD_THREADS;
       if (i < n_quads) {
         int s4 = t.src_al + 4 * i; if (s4 >= L) s4 -= L;
         q[k] = __ldg(reinterpret_cast<const float4*>(x + s4));
@@ -291,7 +299,7 @@ struct Conv1Producer {
     const int n_quads = (t.n + t.mis + 3) >> 2;
 #pragma unroll
     for (int k = 0; k < CONV1_QUADS; ++k) {
-      const int i = ptid + k * NUM_PROD_THREADS;
+      const int i = ptid + k * CONV1_PROD_THREADS;
       if (i < n_quads) {
         const int e0 = 4 * i - t.mis;                               // sample offset of element 0 from ps_lo
         __half* dst = s_win + t.win_off + e0;
@@ -304,7 +312,7 @@ struct Conv1Producer {
   }
   __device__ __forceinline__ static void fill_slabs(uint8_t* stage, int ptid, const __half* s_win, int rows) {
     // rows x 10 chunks (8 in slab 0, 2 in slab 1); rows beyond `rows` keep stale data and are never stored
-    for (int task = ptid; task < rows * 10; task += NUM_PROD_THREADS) {
+    for (int task = ptid; task < rows * 10; task += CONV1_PROD_THREADS) {
       const int r = task / 10, ch = task - r * 10;
       const uint4 v = *reinterpret_cast<const uint4*>(s_win + CONV1_ROW_HOP * r + 8 * ch);
       uint8_t* slab = stage + (ch < 8 ? 0 : A_SLAB_BYTES);
@@ -344,10 +352,14 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const fl
 // the kernel
 // ------------------------------------------------------------------------------------------------
 template <int MODE>   // 0 = conv1, 1 = dw_pw stride 1, 2 = dw_pw stride 2
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr bool kConv1 = (MODE == 0);
   constexpr int kStride = (MODE == 2) ? 2 : 1;
+  using R = Roles<MODE>;
+  constexpr int TC_THREADS = R::THREADS, NUM_EPI_WARPS = R::EPI_WARPS, MMA_WARP = R::MMA_WARP, LOAD_WARP = R::LOAD_WARP,
+                RAW_WARP = R::RAW_WARP, PROD_WARP0 = R::PROD_WARP0;
+  constexpr int kColGroups = NUM_EPI_WARPS / 4;                  // epilogue warps per TMEM lane quarter
   const SmemLayout lay = smem_layout(p, kConv1);
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_base = smem + lay.a_off;
@@ -381,7 +393,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   if (warp == MMA_WARP) {
     if (lane == 0) {
       for (int i = 0; i < MAX_STAGES; ++i) {
-        mbar_init(&a_full[i], kConv1 ? NUM_PROD_THREADS : GROUP_THREADS);
+        mbar_init(&a_full[i], kConv1 ? CONV1_PROD_THREADS : GROUP_THREADS);
         mbar_init(&a_empty[i], 1);
         mbar_init(&raw_full[i], 1);
         mbar_init(&raw_empty[i], GROUP_THREADS);
@@ -404,13 +416,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 
   if (warp < NUM_EPI_WARPS) {
     // =========================== epilogue ===========================
-    // Each warp owns 32 accumulator rows.  Per 64 output channels it converts its rows into a
+    // Each warp owns 32 accumulator rows (TMEM lane quarter warp % 4) and every kColGroups-th 64-column
+    // chunk (column group warp / 4).  Per 64 output channels it converts its rows into a
     // private, 128-byte-swizzled [32 x 64] fp16 box in shared memory (conflict-free 16-byte stores)
     // and one lane hands the box to the TMA store engine: full 128-byte lines leave the SM, rows
     // beyond the tensor (or beyond the clip-view for conv1) are clipped by the tensor map.
     int acc = 0; uint32_t acc_phase = 0;
     uint8_t* my_out = out_base + warp * p.out_bufs * OUT_STAGE_BYTES;
     int obuf = 0;
+    const int quarter = warp & 3, c_first = (warp >> 2) * 64;
+    constexpr int c_step = 64 * kColGroups;
     if (lane == 0) tma_prefetch_desc(&p.tmap_out);
     for (int tile = tile0; tile < p.num_tiles; tile += tstride) {
       mbar_wait(&acc_full[acc], acc_phase);
@@ -421,18 +436,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         const int b = unit / p.vg.n_groups, g = unit - b * p.vg.n_groups;
         rv0 = b * p.n_views;
         m0 = p.vg.start[g]; m1 = p.vg.start[g + 1];
-        row0 = (tile - unit * p.tiles_per_group) * TILE_M + warp * 32;
+        row0 = (tile - unit * p.tiles_per_group) * TILE_M + quarter * 32;
         if (row0 >= p.t_out) m1 = m0;                            // this warp's rows are all past the clip-view's end
       } else {
-        row0 = tile * TILE_M + warp * 32;
+        row0 = tile * TILE_M + quarter * 32;
       }
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(acc * p.ncta);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * p.ncta);
       for (int mem = m0; mem < m1; ++mem) {
         const float gain = kConv1 ? p.vg.gain[mem] : 1.0f;
         const int rv = kConv1 ? rv0 + p.vg.view[mem] : 0;
         uint32_t va[32], vb[32];
-        tmem_ld32(taddr, va);
-        for (int c0 = 0; c0 < p.ncta; c0 += 64) {
+        if (c_first < p.ncta) tmem_ld32(taddr + c_first, va);
+        for (int c0 = c_first; c0 < p.ncta; c0 += c_step) {
           const bool tail = p.ncta - c0 < 64;                    // last 32 columns of a 160- or 96-column slice
           uint8_t* box = my_out + obuf * OUT_STAGE_BYTES;
           if (lane == 0) {                                       // the store that last used this buffer has read it
@@ -445,7 +460,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
             tmem_ld32(taddr + c0 + 32, vb);
             epilogue_chunk<kConv1>(va, s_shift + c0, row_base, 0, lane & 7, gain);
             tmem_ld_wait();
-            if (c0 + 64 < p.ncta) tmem_ld32(taddr + c0 + 64, va);
+            if (c0 + c_step < p.ncta) tmem_ld32(taddr + c0 + c_step, va);
             epilogue_chunk<kConv1>(vb, s_shift + c0 + 32, row_base, 4, lane & 7, gain);
           } else {
             epilogue_chunk<kConv1>(va, s_shift + c0, box + lane * (ROW_BYTES / 2), 0, 0, gain);   // dense 64-byte rows
@@ -578,7 +593,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
           nxt = Conv1Producer::describe(p, next, &x);
           Conv1Producer::load(nxt, x, ptid, q);
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");     // window complete
+        asm volatile("bar.sync 1, %0;" ::"n"(CONV1_PROD_THREADS) : "memory");   // window complete
         mbar_wait(&a_empty[sa], pa ^ 1);
         Conv1Producer::fill_slabs(a_base + sa * p.a_stage_bytes, ptid, win, cur.rows);
         fence_proxy_async_smem();
@@ -768,7 +783,7 @@ int launch_tc_gemm(kws_handle* h, GemmParams& p, cudaStream_t st) {
     if (rc) return rc;
   }
   KWS_T0(h, MODE == 0 ? KC_CONV1 : KC_BLOCK0 + p.block_index, st);
-  tc_gemm_kernel<MODE><<<grid, TC_THREADS, lay.total, st>>>(p);
+  tc_gemm_kernel<MODE><<<grid, Roles<MODE>::THREADS, lay.total, st>>>(p);
   KWS_T1(h, st);
   if (debug_sync() && cudaDeviceSynchronize() != cudaSuccess)
     return fail(h, KWS_ECUDA, "tc_gemm_kernel<" + std::to_string(MODE) + "> cin " + std::to_string(p.cin) + " cout " +
