@@ -65,7 +65,7 @@ constexpr int CONV1_K = 80;                                      // samples per 
 constexpr int CONV1_ROW_HOP = 40;
 constexpr int CONV1_WIN = CONV1_ROW_HOP * (TILE_M - 1) + CONV1_K;   // 5160 staged samples per tile
 constexpr uint32_t CONV1_WIN_BYTES = ((CONV1_WIN + 8) * 2 + 15) & ~15;   // one fp16 window buffer
-constexpr int CONV1_QUADS = 7;                                   // float4 loads per producer thread and tile (1291 quads / 192 threads)
+constexpr int conv1_quads(int threads) { return ((CONV1_WIN + 6) / 4 + threads - 1) / threads; }   // float4 loads per producer thread and tile
 
 
 // TTA views that share a roll shift differ only by the gain, and conv1d_1 is linear and bias-free
@@ -265,16 +265,15 @@ struct Conv1Tile {
   int rows;         // valid rows of the tile
 };
 
-struct Conv1Producer {
-  __device__ __forceinline__ static Conv1Tile describe(const GemmParams& p, int tile, const float** x) {
-    const int unit = tile / p.tiles_per_group, jb = tile - unit * p.tiles_per_group;
-    const int b = unit / p.vg.n_groups, g = unit - b * p.vg.n_groups;
-    const int sm = p.vg.shift[g];
-    *x = p.wav + static_cast<size_t>(b) * L;
+template <int NT>                                                // NT = producer threads
+struct Conv1ProducerT {
+  static constexpr int QUADS = conv1_quads(NT);
+  // window of `rows` output rows starting at conv1d_1 row t_start of a clip rolled by sm samples
+  __device__ __forceinline__ static Conv1Tile make(int sm, int t_start, int rows) {
     Conv1Tile t;
-    t.rows = min(TILE_M, p.t_out - jb * TILE_M);
-    const int p_start = CONV1_ROW_HOP * TILE_M * jb - 10;     // patch stack pads 10 samples on the left
-    const int p_end = min(L, p_start + CONV1_ROW_HOP * (t.rows - 1) + CONV1_K);
+    t.rows = rows;
+    const int p_start = CONV1_ROW_HOP * t_start - 10;         // patch stack pads 10 samples on the left
+    const int p_end = min(L, p_start + CONV1_ROW_HOP * (rows - 1) + CONV1_K);
     t.ps_lo = max(p_start, 0);
     t.n = p_end - t.ps_lo;
     t.win_off = t.ps_lo - p_start;
@@ -283,23 +282,29 @@ struct Conv1Producer {
     t.mis = src & 3;
     return t;
   }
-  __device__ __forceinline__ static void load(const Conv1Tile& t, const float* x, int ptid, float4 (&q)[CONV1_QUADS]) {
+  __device__ __forceinline__ static Conv1Tile describe(const GemmParams& p, int tile, const float** x) {
+    const int unit = tile / p.tiles_per_group, jb = tile - unit * p.tiles_per_group;
+    const int b = unit / p.vg.n_groups, g = unit - b * p.vg.n_groups;
+    *x = p.wav + static_cast<size_t>(b) * L;
+    return make(p.vg.shift[g], jb * TILE_M, min(TILE_M, p.t_out - jb * TILE_M));
+  }
+  __device__ __forceinline__ static void load(const Conv1Tile& t, const float* x, int ptid, float4 (&q)[QUADS]) {
     const int n_quads = (t.n + t.mis + 3) >> 2;
 #pragma unroll
-    for (int k = 0; k < CONV1_QUADS; ++k) {
-      const int i = ptid + k * CONV1_PROD_THREADS;
+    for (int k = 0; k < QUADS; ++k) {
+      const int i = ptid + k * NT;
       if (i < n_quads) {
         int s4 = t.src_al + 4 * i; if (s4 >= L) s4 -= L;
         q[k] = __ldg(reinterpret_cast<const float4*>(x + s4));
       }
     }
   }
-  __device__ __forceinline__ static void store(const Conv1Tile& t, int ptid, const float4 (&q)[CONV1_QUADS], __half* s_win) {
+  __device__ __forceinline__ static void store(const Conv1Tile& t, int ptid, const float4 (&q)[QUADS], __half* s_win) {
     if (ptid < t.win_off) s_win[ptid] = __float2half_rn(0.0f);       // 'SAME' left pad of the patch stack
     const int n_quads = (t.n + t.mis + 3) >> 2;
 #pragma unroll
-    for (int k = 0; k < CONV1_QUADS; ++k) {
-      const int i = ptid + k * CONV1_PROD_THREADS;
+    for (int k = 0; k < QUADS; ++k) {
+      const int i = ptid + k * NT;
       if (i < n_quads) {
         const int e0 = 4 * i - t.mis;                               // sample offset of element 0 from ps_lo
         __half* dst = s_win + t.win_off + e0;
@@ -312,7 +317,7 @@ struct Conv1Producer {
   }
   __device__ __forceinline__ static void fill_slabs(uint8_t* stage, int ptid, const __half* s_win, int rows) {
     // rows x 10 chunks (8 in slab 0, 2 in slab 1); rows beyond `rows` keep stale data and are never stored
-    for (int task = ptid; task < rows * 10; task += CONV1_PROD_THREADS) {
+    for (int task = ptid; task < rows * 10; task += NT) {
       const int r = task / 10, ch = task - r * 10;
       const uint4 v = *reinterpret_cast<const uint4*>(s_win + CONV1_ROW_HOP * r + 8 * ch);
       uint8_t* slab = stage + (ch < 8 ? 0 : A_SLAB_BYTES);
@@ -580,7 +585,8 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
     const int ptid = tid - PROD_WARP0 * 32;
     if constexpr (kConv1) {
       int sa = 0; uint32_t pa = 0, buf = 0;
-      float4 q[CONV1_QUADS];
+      using Conv1Producer = Conv1ProducerT<CONV1_PROD_THREADS>;
+      float4 q[Conv1Producer::QUADS];
       const float* x;
       Conv1Tile cur{}, nxt{};
       int tile = tile0;
@@ -635,6 +641,335 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
   tc_fence_before();
   __syncthreads();
   if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused conv1d_1 + block 1 (model.py:805-812).  The conv1d_1 activation [399, C0] -- the largest
+// tensor of the network -- never leaves the SM: its accumulator is read from TMEM by four
+// "middle" warps that apply gain / BN shift / ReLU6, round to fp16 (the same rounding the
+// unfused path stores) into a swizzled shared-memory row buffer, then run the k=3 depthwise FIR of
+// block 1 over it (each thread slides over 8 consecutive rows of one 8-channel chunk, like
+// produce_slab) and write the UMMA-swizzled A operand of the pointwise GEMM, whose accumulator is
+// drained by four output warps exactly like tc_gemm_kernel.  (A first version did the FIR across
+// lanes with warp shuffles straight from the TMEM rows; it needed ~4x the instructions and the
+// stage is issue-bound.)
+// A tile = 128 conv1d_1 rows -> 126 block-1 rows (stride-1 VALID), 4 tiles per clip-view.
+// TMEM: 2 x C0 columns (conv1d_1 accumulators) + 2 x C1 columns (pointwise accumulators) <= 512.
+//   warps 0-7  middle  : acc1 -> gain, shift, ReLU6, fp16 -> row buffer | FIR -> A2 slabs; two warps per TMEM
+//                        lane quarter, each on half of the channels (this stage is issue/latency-bound: it
+//                        needs two warps per scheduler to hide its own instruction latencies)
+//   warps 8-15 output  : acc2 -> shift, ReLU6, fp16 -> swizzled box -> TMA store; two warps per lane quarter on
+//                        alternate 64-column chunks
+//   warp  16   MMA     : conv1d_1 GEMM (K = 80) once per (clip, view group, tile), pointwise GEMM per view
+//   warp  17   weights : one bulk copy of both weight images (resident)
+//   warps 18-21 window : Conv1Producer (waveform window one tile ahead, swizzled A1 fill)
+// ------------------------------------------------------------------------------------------------
+constexpr int FUSE_ROWS = TILE_M - 2;                            // block-1 rows per tile
+constexpr int FUSE_MID_WARPS = 8, FUSE_OUT_WARP0 = 8, FUSE_OUT_WARPS = 4, FUSE_MMA_WARP = 12, FUSE_W_WARP = 13, FUSE_PROD_WARP0 = 14;
+constexpr int FUSE_PROD_THREADS = 128;
+constexpr int FUSE_THREADS = 32 * FUSE_PROD_WARP0 + FUSE_PROD_THREADS;   // 704
+
+struct alignas(64) FusedParams {
+  CUtensorMap tmap_out;      // block-1 output, 3-D [clip-views, t2, c1], box [64 ch, 32 rows, 1], 128-byte swizzle
+  CUtensorMap tmap_out30;    // same with 30-row boxes: the last lane quarter owns rows 96..125 of a tile only
+  const float* wav;
+  ViewGroups vg;
+  int n_views;
+  const uint8_t* w1_img;     // conv1d_1: 2 slabs of c0 rows (80 folded taps)
+  const uint8_t* w2_img;     // conv1d_2: c0/64 slabs of c1 rows
+  const __half* dw_h;        // depthwise_conv2d_1 taps [3][c0]
+  const float* shift1;       // [c0]
+  const float* shift2;       // [c1]
+  int c0, c1, t1, t2;        // channels; rows per clip-view after conv1d_1 (399) / after block 1 (397)
+  int blocks_per_view;       // ceil(t2 / 126)
+  int num_units;             // clips * view groups * blocks_per_view
+};
+
+struct FusedSmem { uint32_t a1, w1, w2, a2, raw, out, win, sh1, sh2, taps, bars, total; };
+
+__host__ __device__ inline FusedSmem fused_smem(int c0, int c1) {
+  FusedSmem s; uint32_t o = 0;
+  s.a1 = o; o += 2 * A_SLAB_BYTES;
+  s.w1 = o; o += 2u * c0 * ROW_BYTES;
+  s.w2 = o; o += static_cast<uint32_t>(c0 / SLAB_K) * c1 * ROW_BYTES;
+  s.a2 = o; o += static_cast<uint32_t>(c0 / SLAB_K) * A_SLAB_BYTES;     // one stage: the next view's pack phase covers its MMA
+  s.raw = o; o += static_cast<uint32_t>(c0 / SLAB_K) * A_SLAB_BYTES;    // relu6(bn(conv1d_1)) rows of one view, swizzled like a slab
+  s.out = o; o += FUSE_OUT_WARPS * OUT_STAGE_BYTES;                      // (the FIR of the last rows reads 2 rows past a raw slab: into the next region)
+  s.win = o; o += 2 * CONV1_WIN_BYTES;
+  s.sh1 = o; o += c0 * 4u;
+  s.sh2 = o; o += c1 * 4u;
+  s.taps = o; o += (3u * c0 * 2 + 15) & ~15u;
+  s.bars = o; o += 16 * 8 + 16;
+  s.total = o + 1024;
+  return s;
+}
+
+// 8 accumulator values -> gain, shift, ReLU6 -> 8 fp16 (one 16-byte chunk)
+__device__ __forceinline__ uint4 pack8_relu6(const uint32_t* v, const float* sh, float gain) {
+  const __half2 six = __float2half2_rn(6.0f);
+  uint32_t o[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const uint32_t a = pack_relu_f16x2(fmaf(__uint_as_float(v[2 * e]), gain, sh[2 * e]),
+                                       fmaf(__uint_as_float(v[2 * e + 1]), gain, sh[2 * e + 1]));
+    const __half2 ha = __hmin2(*reinterpret_cast<const __half2*>(&a), six);
+    o[e] = *reinterpret_cast<const uint32_t*>(&ha);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+__device__ __forceinline__ uint4 shfl_down4(const uint4& v, int d) {
+  return make_uint4(__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d),
+                    __shfl_down_sync(0xffffffffu, v.z, d), __shfl_down_sync(0xffffffffu, v.w, d));
+}
+
+__global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __grid_constant__ FusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const FusedSmem lay = fused_smem(p.c0, p.c1);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* a1_base = smem + lay.a1;
+  uint8_t* w1_base = smem + lay.w1;
+  uint8_t* w2_base = smem + lay.w2;
+  uint8_t* a2_base = smem + lay.a2;
+  uint8_t* out_base = smem + lay.out;
+  uint8_t* win_base = smem + lay.win;
+  uint8_t* raw_base = smem + lay.raw;
+  float* s_sh1 = reinterpret_cast<float*>(smem + lay.sh1);
+  float* s_sh2 = reinterpret_cast<float*>(smem + lay.sh2);
+  __half* s_taps = reinterpret_cast<__half*>(smem + lay.taps);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bars);
+  uint64_t* a1_full = bars;            // [1]
+  uint64_t* a1_empty = bars + 1;       // [1]
+  uint64_t* acc1_full = bars + 2;      // [2]
+  uint64_t* acc1_empty = bars + 4;     // [2]
+  uint64_t* a2_full = bars + 6;        // [1] (+1 unused)
+  uint64_t* a2_empty = bars + 8;       // [1] (+1 unused)
+  uint64_t* acc2_full = bars + 10;     // [2]
+  uint64_t* acc2_empty = bars + 12;    // [2]
+  uint64_t* w_full = bars + 14;        // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkb2 = p.c0 / SLAB_K;                                // K slabs of the pointwise GEMM
+  const int nch = p.c0 / 8;                                      // 16-byte channel chunks of a conv1d_1 row
+
+  for (int i = tid; i < p.c0; i += FUSE_THREADS) s_sh1[i] = p.shift1[i];
+  for (int i = tid; i < p.c1; i += FUSE_THREADS) s_sh2[i] = p.shift2[i];
+  for (int i = tid; i < 3 * p.c0; i += FUSE_THREADS) s_taps[i] = p.dw_h[i];
+  if (warp == FUSE_MMA_WARP) {
+    if (lane == 0) {
+      mbar_init(a1_full, FUSE_PROD_THREADS);
+      mbar_init(a1_empty, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], FUSE_MID_WARPS * 32);
+        mbar_init(&a2_full[i], FUSE_MID_WARPS * 32); mbar_init(&a2_empty[i], 1);
+        mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], FUSE_OUT_WARPS * 32);
+      }
+      mbar_init(w_full, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc2_col0 = 2u * p.c0;
+
+  auto decode = [&](int unit, int& b, int& g, int& j) {
+    j = unit % p.blocks_per_view;
+    const int ug = unit / p.blocks_per_view;
+    g = ug % p.vg.n_groups;
+    b = ug / p.vg.n_groups;
+  };
+
+  if (warp < FUSE_MID_WARPS) {
+    // =========================== middle: acc1 -> depthwise FIR -> A2 ===========================
+    const int q = warp & 3, hf = warp >> 2;                      // TMEM lane quarter, channel half
+    const int row = q * 32 + lane;
+    const int nchw = nch / 2, ch0 = hf * nchw;                   // pack phase: this warp's 16-byte channel chunks [ch0, ch0 + nchw)
+    const int fkb = tid >> 7, ftg = tid & 127;                   // FIR phase: K slab and (chunk, 8-row run) of this thread
+    const int fc = ftg & 7, fg = ftg >> 3;
+    int n2 = 0, i = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++i) {
+      int b, g, j; decode(unit, b, g, j);
+      const int s1 = i & 1;
+      mbar_wait(&acc1_full[s1], static_cast<uint32_t>(i >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(s1 * p.c0 + ch0 * 8);
+      for (int mem = p.vg.start[g]; mem < p.vg.start[g + 1]; ++mem, ++n2) {
+        const float gain = p.vg.gain[mem];
+        // ---- pack: this row's half of relu6(bn(gain * conv1d_1)) as fp16 into the row buffer ----
+        {
+          uint32_t va[32];
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            if (cc * 4 < nchw) {
+              tmem_ld32(taddr + cc * 32, va);
+              tmem_ld_wait();
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int cg = ch0 + cc * 4 + k;
+                *reinterpret_cast<uint4*>(raw_base + (cg >> 3) * A_SLAB_BYTES + swz_off(row, cg & 7)) =
+                    pack8_relu6(va + 8 * k, s_sh1 + cg * 8, gain);
+              }
+            }
+          }
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(FUSE_MID_WARPS * 32) : "memory");   // all rows of this view are in the buffer
+        mbar_wait(a2_empty, (static_cast<uint32_t>(n2) & 1u) ^ 1u);
+        // ---- depthwise FIR: rows 8 fg .. 8 fg + 7 of chunk fc of K slab fkb (rows 126, 127 are never stored) ----
+        if (fkb < nkb2) {
+          const uint8_t* rsl = raw_base + fkb * A_SLAB_BYTES + (8 * fg) * ROW_BYTES;
+          const int cg = fkb * 8 + fc;
+          const uint4 k0 = *reinterpret_cast<const uint4*>(s_taps + cg * 8);
+          const uint4 k1 = *reinterpret_cast<const uint4*>(s_taps + p.c0 + cg * 8);
+          const uint4 k2 = *reinterpret_cast<const uint4*>(s_taps + 2 * p.c0 + cg * 8);
+          uint4 x[10];
+#pragma unroll
+          for (int r = 0; r < 10; ++r) x[r] = lds128(rsl + r * ROW_BYTES + ((fc ^ (r & 7)) << 4));
+          uint8_t* dst = a2_base + fkb * A_SLAB_BYTES + (8 * fg) * ROW_BYTES;
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            *reinterpret_cast<uint4*>(dst + r * ROW_BYTES + ((fc ^ r) << 4)) = fir3(x[r], x[r + 1], x[r + 2], k0, k1, k2);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(a2_full);
+        asm volatile("bar.sync 2, %0;" ::"n"(FUSE_MID_WARPS * 32) : "memory");   // the buffer may be overwritten
+      }
+      tc_fence_before();
+      mbar_arrive(&acc1_empty[s1]);
+    }
+  } else if (warp < FUSE_MMA_WARP) {
+    // =========================== output: acc2 -> BN shift, ReLU6 -> TMA store ===========================
+    const int ow = warp - FUSE_OUT_WARP0;
+    const int q = ow & 3, c_first = (ow >> 2) * 64;              // TMEM lane quarter; first 64-column chunk
+    constexpr int c_step = 64 * (FUSE_OUT_WARPS / 4);
+    uint8_t* box = out_base + ow * OUT_STAGE_BYTES;               // one store box per warp
+    uint8_t* row_base = box + lane * ROW_BYTES;
+    int n2 = 0;
+    if (lane == 0) { tma_prefetch_desc(&p.tmap_out); tma_prefetch_desc(&p.tmap_out30); }
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      int b, g, j; decode(unit, b, g, j);
+      const int row0 = j * FUSE_ROWS + q * 32;                   // first block-1 row of this warp's box
+      for (int mem = p.vg.start[g]; mem < p.vg.start[g + 1]; ++mem, ++n2) {
+        const int s2 = n2 & 1;
+        mbar_wait(&acc2_full[s2], static_cast<uint32_t>(n2 >> 1) & 1u);
+        tc_fence_after();
+        if (row0 < p.t2) {
+          const int rv = b * p.n_views + p.vg.view[mem];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc2_col0 + static_cast<uint32_t>(s2 * p.c1);
+          for (int c0 = c_first; c0 < p.c1; c0 += c_step) {
+            uint32_t va[32];                                     // one 32-column buffer keeps the kernel under 80 registers
+            tmem_ld32(taddr + c0, va);
+            if (lane == 0) bulk_wait_group_read<0>();            // the previous store has read the box
+            __syncwarp();
+            tmem_ld_wait();
+            epilogue_chunk<false>(va, s_sh2 + c0, row_base, 0, lane & 7, 1.0f);
+            tmem_ld32(taddr + c0 + 32, va);
+            tmem_ld_wait();
+            epilogue_chunk<false>(va, s_sh2 + c0 + 32, row_base, 4, lane & 7, 1.0f);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(q == 3 ? &p.tmap_out30 : &p.tmap_out, c0, row0, rv, box);
+              bulk_commit_group();
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&acc2_empty[s2]);
+      }
+    }
+    if (lane == 0) bulk_wait_group_all();
+  } else if (warp == FUSE_MMA_WARP) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const uint32_t idesc1 = umma_idesc_f16(TILE_M, p.c0, /*fp16*/ 0);
+      const uint32_t idesc2 = umma_idesc_f16(TILE_M, p.c1, /*fp16*/ 0);
+      const uint32_t a1 = smem_u32(a1_base), w1 = smem_u32(w1_base), w2 = smem_u32(w2_base), a2 = smem_u32(a2_base);
+      mbar_wait(w_full, 0);
+      uint32_t ph_a1 = 0;
+      auto issue_conv1 = [&](int i) {                            // conv1d_1 GEMM of this CTA's i-th unit
+        const int s1 = i & 1;
+        mbar_wait(&acc1_empty[s1], (static_cast<uint32_t>(i >> 1) & 1u) ^ 1u);
+        mbar_wait(a1_full, ph_a1); ph_a1 ^= 1u;
+        tc_fence_after();
+        const uint32_t d = tmem_base + static_cast<uint32_t>(s1 * p.c0);
+        for (int ks = 0; ks < 4; ++ks)
+          umma_f16(d, umma_desc_sw128(a1 + ks * 32), umma_desc_sw128(w1 + ks * 32), idesc1, ks != 0 ? 1u : 0u);
+        umma_f16(d, umma_desc_sw128(a1 + A_SLAB_BYTES), umma_desc_sw128(w1 + p.c0 * ROW_BYTES), idesc1, 1u);   // samples 64..79
+        umma_commit(a1_empty);
+        umma_commit(&acc1_full[s1]);
+      };
+      int i = 0, n2 = 0;
+      if (static_cast<int>(blockIdx.x) < p.num_units) issue_conv1(0);
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++i) {
+        if (unit + static_cast<int>(gridDim.x) < p.num_units) issue_conv1(i + 1);   // next tile's conv1d_1 runs under this tile's views
+        int b, g, j; decode(unit, b, g, j);
+        for (int mem = p.vg.start[g]; mem < p.vg.start[g + 1]; ++mem, ++n2) {
+          const int s2 = n2 & 1;
+          const uint32_t ph2 = static_cast<uint32_t>(n2 >> 1) & 1u;
+          mbar_wait(&acc2_empty[s2], ph2 ^ 1u);
+          mbar_wait(a2_full, static_cast<uint32_t>(n2) & 1u);
+          tc_fence_after();
+          const uint32_t d = tmem_base + acc2_col0 + static_cast<uint32_t>(s2 * p.c1);
+          const uint32_t a = a2;
+          for (int kb = 0; kb < nkb2; ++kb)
+            for (int ks = 0; ks < 4; ++ks)
+              umma_f16(d, umma_desc_sw128(a + kb * A_SLAB_BYTES + ks * 32),
+                       umma_desc_sw128(w2 + kb * p.c1 * ROW_BYTES + ks * 32), idesc2, (kb | ks) != 0 ? 1u : 0u);
+          umma_commit(a2_empty);
+          umma_commit(&acc2_full[s2]);
+        }
+      }
+    }
+  } else if (warp == FUSE_W_WARP) {
+    // =========================== weights (resident) ===========================
+    if (lane == 0) {
+      const uint32_t b1 = 2u * p.c0 * ROW_BYTES, b2 = static_cast<uint32_t>(nkb2) * p.c1 * ROW_BYTES;
+      mbar_arrive_expect_tx(w_full, b1 + b2);
+      for (uint32_t o = 0; o < b1; o += 16384) bulk_g2s(w1_base + o, p.w1_img + o, min(16384u, b1 - o), w_full);
+      for (uint32_t o = 0; o < b2; o += 16384) bulk_g2s(w2_base + o, p.w2_img + o, min(16384u, b2 - o), w_full);
+    }
+  } else {
+    // =========================== waveform window producers ===========================
+    using Conv1Producer = Conv1ProducerT<FUSE_PROD_THREADS>;
+    const int ptid = tid - FUSE_PROD_WARP0 * 32;
+    uint32_t pe = 0, buf = 0;
+    float4 qd[Conv1Producer::QUADS];
+    const float* x = nullptr;
+    Conv1Tile cur{}, nxt{};
+    auto describe = [&](int unit) {
+      int b, g, j; decode(unit, b, g, j);
+      x = p.wav + static_cast<size_t>(b) * L;
+      return Conv1Producer::make(p.vg.shift[g], j * FUSE_ROWS, min(TILE_M, p.t1 - j * FUSE_ROWS));
+    };
+    int unit = blockIdx.x;
+    if (unit < p.num_units) { cur = describe(unit); Conv1Producer::load(cur, x, ptid, qd); }
+    for (; unit < p.num_units; unit += gridDim.x) {
+      __half* win = reinterpret_cast<__half*>(win_base + buf * CONV1_WIN_BYTES);
+      Conv1Producer::store(cur, ptid, qd, win);
+      const int next = unit + gridDim.x;
+      if (next < p.num_units) { nxt = describe(next); Conv1Producer::load(nxt, x, ptid, qd); }
+      asm volatile("bar.sync 1, %0;" ::"n"(FUSE_PROD_THREADS) : "memory");    // window complete
+      mbar_wait(a1_empty, pe ^ 1u);
+      Conv1Producer::fill_slabs(a1_base, ptid, win, cur.rows);
+      fence_proxy_async_smem();
+      mbar_arrive(a1_full);
+      pe ^= 1u; buf ^= 1u;
+      cur = nxt;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == FUSE_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
@@ -796,6 +1131,50 @@ int launch_tc_gemm(kws_handle* h, GemmParams& p, cudaStream_t st) {
   return KWS_OK;
 }
 
+int launch_conv1_block1(kws_handle* h, Model& m, const float* wav, int nb, const ViewGroups& vg, int V, __half* out,
+                        cudaStream_t st) {
+  const LayerDesc& d = m.layers[0];
+  FusedParams p{};
+  p.wav = wav; p.vg = vg; p.n_views = V;
+  p.w1_img = reinterpret_cast<const uint8_t*>(m.tc_conv1);
+  p.w2_img = reinterpret_cast<const uint8_t*>(m.tc_pw[0]);
+  p.dw_h = m.tc_dw[0];
+  p.shift1 = m.bn_shift[0]; p.shift2 = m.bn_shift[1];
+  p.c0 = m.c0; p.c1 = d.cout; p.t1 = m.t0; p.t2 = d.t_out;
+  p.blocks_per_view = (p.t2 + FUSE_ROWS - 1) / FUSE_ROWS;
+  p.num_units = nb * vg.n_groups * p.blocks_per_view;
+  const int rows = nb * V;
+  int rc = make_tensor_map(h, &p.tmap_out, out, p.c1, p.t2, std::max(rows, 2), 32, true);
+  if (rc) return rc;
+  rc = make_tensor_map(h, &p.tmap_out30, out, p.c1, p.t2, std::max(rows, 2), 30, true);
+  if (rc) return rc;
+  const FusedSmem lay = fused_smem(p.c0, p.c1);
+  if (static_cast<int>(lay.total) > SMEM_LIMIT) return fail(h, KWS_EUNSUPPORTED, "fused conv1d_1 + block 1 does not fit in shared memory");
+  static bool attr_set = false;
+  if (!attr_set) {
+    KWS_CUDA(h, cudaFuncSetAttribute(conv1_block1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    attr_set = true;
+  }
+  const int grid = std::min(p.num_units, h->num_sms);
+  if (grid <= 0) return KWS_OK;
+  KWS_T0(h, KC_CONV1, st);
+  conv1_block1_kernel<<<grid, FUSE_THREADS, lay.total, st>>>(p);
+  KWS_T1(h, st);
+  if (debug_sync() && cudaDeviceSynchronize() != cudaSuccess)
+    return fail(h, KWS_ECUDA, std::string("conv1_block1_kernel: ") + cudaGetErrorString(cudaGetLastError()));
+  KWS_LAUNCH_CHECK(h);
+  return KWS_OK;
+}
+
+// conv1d_1 and block 1 run as one kernel when the shapes allow it (both shipped architectures);
+// KWS_NO_FUSE=1 keeps them separate (A/B and layer-0 debugging).
+bool fuse_conv1_block1(const Model& m) {
+  static const bool off = [] { const char* e = getenv("KWS_NO_FUSE"); return e && e[0] == '1'; }();
+  const LayerDesc& d = m.layers[0];
+  return !off && d.stride == 1 && d.cin == m.c0 && m.c0 % SLAB_K == 0 && m.c0 <= 128 && d.cout % 64 == 0 &&
+         2 * m.c0 + 2 * d.cout <= TMEM_COLS && d.t_out == m.t0 - 2;
+}
+
 }  // namespace
 
 int model_build_tc(kws_handle* h, Model& m, const std::vector<std::vector<float>>& pw_host,
@@ -864,7 +1243,13 @@ int launch_forward_tc(kws_handle* h, Model& m, const float* wav, int B, const Vi
     const int rows = nb * V;
     __half* cur = static_cast<__half*>(h->act[0]);
     __half* nxt = static_cast<__half*>(h->act[1]);
-    {
+    const bool fused = dbg_layer != 0 && fuse_conv1_block1(m);
+    if (fused) {
+      int rc = launch_conv1_block1(h, m, wav + static_cast<size_t>(b0) * L, nb, vg, V, cur, st);
+      if (rc) return rc;
+      if (dbg_layer == 1)
+        return launch_to_float(h, cur, true, dbg_out, static_cast<size_t>(rows) * m.layers[0].t_out * m.layers[0].cout, st);
+    } else {
       GemmParams p{};
       p.wav = wav + static_cast<size_t>(b0) * L; p.n_views = V;
       p.vg = vg;
@@ -880,7 +1265,7 @@ int launch_forward_tc(kws_handle* h, Model& m, const float* wav, int B, const Vi
       if (rc) return rc;
     }
     if (dbg_layer == 0) return launch_to_float(h, cur, true, dbg_out, static_cast<size_t>(rows) * m.t0 * m.c0, st);
-    for (int i = 0; i < NUM_BLOCKS; ++i) {
+    for (int i = fused ? 1 : 0; i < NUM_BLOCKS; ++i) {
       const LayerDesc& d = m.layers[i];
       if (d.cin % SLAB_K) return fail(h, KWS_EUNSUPPORTED, "channel count must be a multiple of 64");
       GemmParams p{};
