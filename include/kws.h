@@ -73,6 +73,9 @@ void kws_destroy(kws_t* h);
 const char* kws_last_error(const kws_t* h);
 int  kws_abi_version(void);
 int  kws_set_precision(kws_t* h, int precision);          /* KWS_PREC_*  (default TC) */
+/* Tensor-core tier only: run conv1d_1 and the first depthwise-separable block (model.py:805-812) as ONE
+ * kernel (default 1).  0 keeps them as two launches -- same results, more HBM traffic; used for A/B. */
+int  kws_set_fusion(kws_t* h, int on);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t kws_launch_count(const kws_t* h);
 

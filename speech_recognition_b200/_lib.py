@@ -30,6 +30,7 @@ SIGNATURES = {
     "kws_destroy": (None, [_vp]),
     "kws_last_error": (C.c_char_p, [_vp]),
     "kws_set_precision": (_i, [_vp, _i]),
+    "kws_set_fusion": (_i, [_vp, _i]),
     "kws_launch_count": (_i64, [_vp]),
     "kws_timing_enable": (_i, [_vp, _i]),
     "kws_timing_read": (_i, [_vp, C.POINTER(_d), C.POINTER(_i64), _i]),

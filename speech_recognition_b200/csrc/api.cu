@@ -185,6 +185,12 @@ int kws_set_precision(kws_t* h, int precision) {
   return KWS_OK;
 }
 
+int kws_set_fusion(kws_t* h, int on) {
+  if (!h) return KWS_EINVAL;
+  h->fuse_conv1_block1 = on != 0;
+  return KWS_OK;
+}
+
 int kws_set_noise_bank(kws_t* h, const float* bank, const int64_t* file_offsets_h, int n_files) {
   if (!h) return KWS_EINVAL;
   if (n_files < 0 || (n_files > 0 && (!bank || !file_offsets_h))) return fail(h, KWS_EINVAL, "bad noise bank");

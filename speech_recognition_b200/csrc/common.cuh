@@ -73,6 +73,7 @@ struct kws_handle {
   int device = 0;
   int max_rows = 0;
   int precision = KWS_PREC_TC;
+  bool fuse_conv1_block1 = true;
   int num_sms = kws::NUM_SMS_B200;
   std::string err;
   int64_t launches = 0;

@@ -1243,7 +1243,7 @@ int launch_forward_tc(kws_handle* h, Model& m, const float* wav, int B, const Vi
     const int rows = nb * V;
     __half* cur = static_cast<__half*>(h->act[0]);
     __half* nxt = static_cast<__half*>(h->act[1]);
-    const bool fused = dbg_layer != 0 && fuse_conv1_block1(m);
+    const bool fused = dbg_layer != 0 && h->fuse_conv1_block1 && fuse_conv1_block1(m);
     if (fused) {
       int rc = launch_conv1_block1(h, m, wav + static_cast<size_t>(b0) * L, nb, vg, V, cur, st);
       if (rc) return rc;

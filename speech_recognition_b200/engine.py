@@ -68,6 +68,10 @@ class Engine:
         self._check(self.lib.kws_set_precision(self.h, int(p)))
         self.precision = p
 
+    def set_fusion(self, on: bool):
+        """conv1d_1 + block 1 as one kernel (default) or two (tensor-core tier)."""
+        self._check(self.lib.kws_set_fusion(self.h, int(bool(on))))
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.kws_launch_count(self.h))

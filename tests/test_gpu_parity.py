@@ -324,3 +324,30 @@ def test_forward_tc(engine, arch, views):
     confident = (margin[:, -1] - margin[:, -2]) > 0.1              # labels may only flip on near-ties
     assert (amax.cpu().numpy()[confident] == r_pred[confident]).all()
     assert (amax.cpu().numpy() == r_pred).mean() >= 0.97
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("arch", [195, 106])
+def test_fused_and_unfused_first_block_agree(engine, arch):
+    """conv1d_1 + block 1 as one kernel (default) vs two launches: the fused kernel rounds the
+    conv1d_1 activation to fp16 exactly where the unfused path stores it, so block-1 activations
+    and the final probabilities must agree to fp16 rounding noise (TTA gains included)."""
+    w = synth.synthetic_weights(arch)
+    engine.load_model(0, arch, w)
+    x = dev(synth.make_clips(24, seed=77 + arch))
+    c1 = 128
+    engine.set_precision("tc")
+    try:
+        a_f = engine.debug_activation(x, 1, (397, c1), views=TTA_8).cpu().numpy()
+        p_f, l_f = engine.forward(x, views=TTA_8)
+        engine.set_fusion(False)
+        a_u = engine.debug_activation(x, 1, (397, c1), views=TTA_8).cpu().numpy()
+        p_u, l_u = engine.forward(x, views=TTA_8)
+    finally:
+        engine.set_fusion(True)
+        engine.set_precision("fp32")
+    d = np.abs(a_f - a_u)
+    # conv(fp16(x)) * gain (both paths) -> identical up to the order of fp32 accumulation inside the MMA
+    assert d.max() < 2e-2 and d.mean() < 1e-4, (d.max(), d.mean())
+    assert np.abs(p_f.cpu().numpy() - p_u.cpu().numpy()).max() < 2e-3
+    assert (l_f.cpu().numpy() == l_u.cpu().numpy()).mean() >= 0.95
