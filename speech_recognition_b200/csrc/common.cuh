@@ -51,6 +51,9 @@ struct Model {
 struct Frontend {
   bool configured = false;
   int win = 0, hop = 0, n_fft = 0, n_bins = 0, frames = 0, n_mel = 0, n_keep = 0;
+  // flavour: 0 = tf.contrib.signal chain of input_data.py:361-381 (magnitude, log(x + 1e-6));
+  //          1 = native contrib_audio ops of audio.py:15-23 (power spectrogram, log(max(x, 1e-12)))
+  int flavour = 0;
   float* blob = nullptr;
   float* dft_basis = nullptr;             // [win, 2*n_bins] interleaved (cos*w, -sin*w)
   float* mel_w = nullptr;                 // [n_bins, n_mel]
@@ -142,7 +145,7 @@ int launch_augment(kws_handle* h, const float* wav, const int16_t* pcm, float pc
                    const float* bg_vol, const float* fg_vol, float* out, int B, int clamp,
                    cudaStream_t st);
 int frontend_build(kws_handle* h, int win, int hop, int n_mel, int n_keep, float f_lo, float f_hi,
-                   int sample_rate);
+                   int sample_rate, int flavour = 0);
 int launch_features_f32(kws_handle* h, const float* wav, int B, int kind, float* out, cudaStream_t st);
 int launch_features_tc(kws_handle* h, const float* wav, int B, int kind, float* out, cudaStream_t st);
 int model_build(kws_handle* h, int slot, int arch, const kws_tensor_h* t, int n);

@@ -154,8 +154,8 @@ struct EpiBnRelu6 {          // BatchNorm (inference) + ReLU6, model.py:50-51 / 
   }
 };
 
-struct EpiMagnitude {        // columns (2j, 2j+1) = (re, im) of bin j -> |X| (input_data.py:366)
-  float* S; int n_bins;
+struct EpiMagnitude {        // columns (2j, 2j+1) = (re, im) of bin j -> |X| (input_data.py:366), or |X|^2 (audio.py:15-19)
+  float* S; int n_bins; bool power;
   __device__ __forceinline__ void operator()(int m, int n, float (&acc)[G_TM][G_TN], int M, int N) const {
 #pragma unroll
     for (int i = 0; i < G_TM; ++i)
@@ -164,20 +164,22 @@ struct EpiMagnitude {        // columns (2j, 2j+1) = (re, im) of bin j -> |X| (i
         const int bin = (n + j) >> 1;
         if (m + i < M && bin < n_bins) {
           const float re = acc[i][j], im = acc[i][j + 1];
-          S[static_cast<size_t>(m + i) * n_bins + bin] = sqrtf(fmaf(re, re, im * im));
+          const float pw = fmaf(re, re, im * im);
+          S[static_cast<size_t>(m + i) * n_bins + bin] = power ? pw : sqrtf(pw);
         }
       }
   }
 };
 
-struct EpiLog {              // log(mel + 1e-6)  (input_data.py:378)
-  float* C; int ldc;
+struct EpiLog {              // log(mel + 1e-6)  (input_data.py:378), or log(max(mel, 1e-12)) (contrib_audio Mfcc)
+  float* C; int ldc; bool floor_mode;
   __device__ __forceinline__ void operator()(int m, int n, float (&acc)[G_TM][G_TN], int M, int N) const {
 #pragma unroll
     for (int i = 0; i < G_TM; ++i)
 #pragma unroll
       for (int j = 0; j < G_TN; ++j)
-        if (m + i < M && n + j < N) C[static_cast<size_t>(m + i) * ldc + n + j] = logf(acc[i][j] + 1e-6f);
+        if (m + i < M && n + j < N)
+          C[static_cast<size_t>(m + i) * ldc + n + j] = floor_mode ? logf(fmaxf(acc[i][j], 1e-12f)) : logf(acc[i][j] + 1e-6f);
   }
 };
 
