@@ -110,6 +110,14 @@ int kws_augment_pcm16(kws_t* h, const int16_t* pcm, float divisor, const int32_t
 int kws_frontend_config(kws_t* h, int window_size_samples, int window_stride_samples,
                         int n_mel, int n_keep, float lower_edge_hertz, float upper_edge_hertz,
                         int sample_rate);
+/* Native contrib_audio flavour of the same stage (audio.py:15-23, exp-106 graph nodes AudioSpectrogram / Mfcc):
+ * contrib_audio.audio_spectrogram(window_size, stride, magnitude_squared=True) + contrib_audio.mfcc(
+ * dct_coefficient_count; TF defaults lower 20 Hz, upper 4000 Hz, 40 filterbank channels).  After this call
+ * kws_features(kind = SPEC) returns the POWER spectrogram, LOGMEL log(max(mel, 1e-12)) of the HTK-style bank
+ * applied to sqrt(power), MFCC its sqrt(2/N)-normalised DCT-II.  TF's C++ kernels are un-vendored: the
+ * algorithm follows spectrogram.cc / mfcc_mel_filterbank.cc / mfcc_dct.cc as published (parity unpinned). */
+int kws_frontend_config_contrib(kws_t* h, int window_size, int stride, int sample_rate, float lower_hz,
+                                float upper_hz, int filterbank_channels, int dct_coefficient_count);
 int kws_frontend_frames(const kws_t* h);   /* spectrogram_length (98) */
 /* Replaces sess.run(spectrogram_ | mfcc_) (input_data.py:520-531). */
 int kws_features(kws_t* h, const float* wav, int B, int kind, float* out, void* stream);

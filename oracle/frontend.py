@@ -118,3 +118,68 @@ def features(x: np.ndarray, *, window_size_samples: int = 480,
     mf = mfcc_from_log_mel(lm, fft_dtype)
     K = num_log_mel_features if num_log_mel_features is not None else dct_coefficient_count
     return mf[..., :K]
+
+
+# ------------------------------------------------------------------------------------------------
+# Native contrib_audio flavour (audio.py:15-23; exp-106 graph nodes AudioSpectrogram / Mfcc).
+# TF 1.4's C++ kernels are not vendored in the reference; this restates their published algorithm
+# (tensorflow/core/kernels/spectrogram.cc, mfcc.cc, mfcc_mel_filterbank.cc, mfcc_dct.cc), which
+# computes in double precision and casts to float at the end.  PARITY UNPINNED: no golden vector
+# of these ops exists in the reference.
+# ------------------------------------------------------------------------------------------------
+def contrib_audio_spectrogram(x, window_size=480, stride=160, magnitude_squared=True):
+    """x [B, L] f32 -> [B, frames, fft/2+1]; periodic Hann in double, zero-pad to the next power of two."""
+    x = np.asarray(x, F32).astype(np.float64)
+    w = 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(window_size) / window_size)
+    fr = frame(x, window_size, stride) * w
+    n_fft = next_pow2(window_size)
+    spec = np.fft.rfft(fr, n=n_fft, axis=-1)
+    p = spec.real ** 2 + spec.imag ** 2
+    return (p if magnitude_squared else np.sqrt(p)).astype(F32)
+
+
+def contrib_mel_filterbank(input_length=257, sample_rate=16000.0, channels=40, lower=20.0, upper=4000.0):
+    """(band_mapper, weights, start_index, end_index) of MfccMelFilterbank::Initialize."""
+    mel = lambda f: 1127.0 * np.log1p(f / 700.0)  # noqa: E731
+    mel_low, mel_hi = mel(lower), mel(upper)
+    spacing = (mel_hi - mel_low) / (channels + 1)
+    center = mel_low + spacing * (np.arange(channels + 1) + 1)
+    hz_per_sbin = 0.5 * sample_rate / (input_length - 1)
+    start, end = int(1.5 + lower / hz_per_sbin), int(upper / hz_per_sbin)
+    band = np.full(input_length, -2, np.int64)
+    wts = np.zeros(input_length, np.float64)
+    ch = 0
+    for i in range(input_length):
+        melf = mel(i * hz_per_sbin)
+        if i < start or i > end:
+            continue
+        while ch < channels and center[ch] < melf:
+            ch += 1
+        band[i] = ch - 1
+        c = band[i]
+        wts[i] = (center[c + 1] - melf) / (center[c + 1] - center[c]) if c >= 0 else \
+            (center[0] - melf) / (center[0] - mel_low)
+    return band, wts, start, end
+
+
+def contrib_mfcc(power_spec, sample_rate=16000, dct_coefficient_count=40, channels=40, lower=20.0,
+                 upper=4000.0, return_log_mel=False):
+    """contrib_audio.mfcc on a squared-magnitude spectrogram [.., frames, bins] -> [.., frames, dct_count]."""
+    p = np.asarray(power_spec, F32).astype(np.float64)
+    bins = p.shape[-1]
+    band, wts, start, end = contrib_mel_filterbank(bins, sample_rate, channels, lower, upper)
+    out = np.zeros(p.shape[:-1] + (channels,), np.float64)
+    for i in range(start, end + 1):                       # MfccMelFilterbank::Compute
+        sv = np.sqrt(p[..., i])
+        wv = sv * wts[i]
+        c = band[i]
+        if c >= 0:
+            out[..., c] += wv
+        if c + 1 < channels:
+            out[..., c + 1] += sv - wv
+    lm = np.log(np.maximum(out, 1e-12))                   # kFilterbankFloor
+    if return_log_mel:
+        return lm.astype(F32)
+    n = channels                                          # MfccDct
+    cos = np.sqrt(2.0 / n) * np.cos(np.arange(dct_coefficient_count)[:, None] * (np.pi / n) * (np.arange(n)[None, :] + 0.5))
+    return (lm @ cos.T).astype(F32)

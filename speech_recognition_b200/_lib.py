@@ -38,6 +38,7 @@ SIGNATURES = {
     "kws_augment": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "kws_augment_pcm16": (_i, [_vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "kws_frontend_config": (_i, [_vp, _i, _i, _i, _i, _f, _f, _i]),
+    "kws_frontend_config_contrib": (_i, [_vp, _i, _i, _i, _f, _f, _i, _i]),
     "kws_frontend_frames": (_i, [_vp]),
     "kws_features": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "kws_model_load": (_i, [_vp, _i, _i, C.POINTER(TensorH), _i]),

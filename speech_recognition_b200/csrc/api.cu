@@ -242,6 +242,14 @@ int kws_frontend_config(kws_t* h, int win, int hop, int n_mel, int n_keep, float
   return frontend_build(h, win, hop, n_mel, n_keep, f_lo, f_hi, sample_rate);
 }
 
+int kws_frontend_config_contrib(kws_t* h, int window_size, int stride, int sample_rate, float lower_hz,
+                                float upper_hz, int filterbank_channels, int dct_coefficient_count) {
+  if (!h) return KWS_EINVAL;
+  KWS_CUDA(h, cudaSetDevice(h->device));
+  return frontend_build(h, window_size, stride, filterbank_channels, dct_coefficient_count, lower_hz, upper_hz,
+                        sample_rate, /*flavour=*/1);
+}
+
 int kws_frontend_frames(const kws_t* h) { return (h && h->fe.configured) ? h->fe.frames : 0; }
 
 int kws_features(kws_t* h, const float* wav, int B, int kind, float* out, void* stream) {

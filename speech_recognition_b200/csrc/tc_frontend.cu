@@ -55,6 +55,7 @@ struct DftParams {
   const float* dct;          // [n_mel][64] zero padded
   int frames, hop, win, n_mel, n_keep;
   int rows_total, num_tiles, num_kb, last_ksteps;
+  int floor_mode;            // 0: log(mel + 1e-6) (input_data.py:378); 1: log(max(mel, 1e-12)) (contrib_audio Mfcc)
 };
 
 struct FSmem { uint32_t a_off, b_off, tab_off, dct_off, bar_off, total; };
@@ -70,7 +71,7 @@ __host__ __device__ inline FSmem f_smem(int n_mel, bool mfcc) {
   return s;
 }
 
-template <bool MFCC>
+template <bool MFCC, bool FLOOR>
 __global__ void __launch_bounds__(F_THREADS, 1) stft_mel_tc_kernel(const DftParams p) {
   extern __shared__ uint8_t smem_raw[];
   const FSmem lay = f_smem(p.n_mel, MFCC);
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) stft_mel_tc_kernel(const DftPara
 #pragma unroll
       for (int k = 0; k < (MFCC ? F_DCT_LD : 1); ++k) dctacc[k] = 0.0f;
       auto emit = [&]() {
-        const float lm = logf(acc_a + 1e-6f);                  // input_data.py:378
+        const float lm = FLOOR ? logf(fmaxf(acc_a, 1e-12f)) : logf(acc_a + 1e-6f);   // TF mfcc.cc / input_data.py:378
         if (MFCC) {
           const float4* d4 = reinterpret_cast<const float4*>(s_dct + m_cur * F_DCT_LD);
 #pragma unroll
@@ -383,19 +384,27 @@ int launch_features_tc(kws_handle* h, const float* wav, int B, int kind, float* 
   p.rows_total = B * fe.frames;
   p.num_tiles = (p.rows_total + TILE_M - 1) / TILE_M;
   p.num_kb = fe.tc_kblocks; p.last_ksteps = fe.tc_last_ksteps;
+  p.floor_mode = fe.flavour == 1;
   const bool mfcc = kind == KWS_FEAT_MFCC;
   const FSmem lay = f_smem(fe.n_mel, mfcc);
   if (static_cast<int>(lay.total) > F_SMEM_LIMIT) return launch_features_f32(h, wav, B, kind, out, st);
   static bool attr_set = false;
   if (!attr_set) {
-    KWS_CUDA(h, cudaFuncSetAttribute(stft_mel_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_LIMIT));
-    KWS_CUDA(h, cudaFuncSetAttribute(stft_mel_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_LIMIT));
+    KWS_CUDA(h, cudaFuncSetAttribute(stft_mel_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_LIMIT));
+    KWS_CUDA(h, cudaFuncSetAttribute(stft_mel_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_LIMIT));
+    KWS_CUDA(h, cudaFuncSetAttribute(stft_mel_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_LIMIT));
+    KWS_CUDA(h, cudaFuncSetAttribute(stft_mel_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_LIMIT));
     attr_set = true;
   }
   const int grid = std::min(p.num_tiles, h->num_sms);
   KWS_T0(h, KC_DFT, st);
-  if (mfcc) stft_mel_tc_kernel<true><<<grid, F_THREADS, lay.total, st>>>(p);
-  else stft_mel_tc_kernel<false><<<grid, F_THREADS, lay.total, st>>>(p);
+  if (p.floor_mode) {
+    if (mfcc) stft_mel_tc_kernel<true, true><<<grid, F_THREADS, lay.total, st>>>(p);
+    else stft_mel_tc_kernel<false, true><<<grid, F_THREADS, lay.total, st>>>(p);
+  } else {
+    if (mfcc) stft_mel_tc_kernel<true, false><<<grid, F_THREADS, lay.total, st>>>(p);
+    else stft_mel_tc_kernel<false, false><<<grid, F_THREADS, lay.total, st>>>(p);
+  }
   KWS_T1(h, st);
   KWS_LAUNCH_CHECK(h);
   return KWS_OK;

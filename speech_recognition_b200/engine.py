@@ -124,6 +124,16 @@ class Engine:
         self.fe = dict(frames=int(self.lib.kws_frontend_frames(self.h)),
                        bins=(1 << (window_size_samples - 1).bit_length()) // 2 + 1, n_mel=n_mel, n_keep=n_keep)
 
+    def frontend_config_contrib(self, window_size=480, stride=160, sample_rate=16000, lower_frequency_limit=20.0,
+                                upper_frequency_limit=4000.0, filterbank_channel_count=40, dct_coefficient_count=40):
+        """contrib_audio.audio_spectrogram(magnitude_squared=True) + contrib_audio.mfcc flavour (audio.py:15-23)."""
+        self._check(self.lib.kws_frontend_config_contrib(self.h, window_size, stride, sample_rate,
+                                                         lower_frequency_limit, upper_frequency_limit,
+                                                         filterbank_channel_count, dct_coefficient_count))
+        self.fe = dict(frames=int(self.lib.kws_frontend_frames(self.h)),
+                       bins=(1 << (window_size - 1).bit_length()) // 2 + 1, n_mel=filterbank_channel_count,
+                       n_keep=dct_coefficient_count)
+
     def feature_shape(self, kind):
         k = _KIND.get(kind, kind)
         d = {FEAT_SPEC: self.fe["bins"], FEAT_LOGMEL: self.fe["n_mel"], FEAT_MFCC: self.fe["n_keep"]}[k]

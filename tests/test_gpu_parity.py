@@ -351,3 +351,45 @@ def test_fused_and_unfused_first_block_agree(engine, arch):
     assert d.max() < 2e-2 and d.mean() < 1e-4, (d.max(), d.mean())
     assert np.abs(p_f.cpu().numpy() - p_u.cpu().numpy()).max() < 2e-3
     assert (l_f.cpu().numpy() == l_u.cpu().numpy()).mean() >= 0.95
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tc"])
+def test_contrib_audio_frontend(engine, prec):
+    """Native contrib_audio flavour (audio.py:15-23): power spectrogram, HTK-style 20-4000 Hz bank on sqrt(power),
+    log(max(., 1e-12)), sqrt(2/N) DCT -- against the restatement of TF's published C++ algorithm (float64)."""
+    x = synth.make_clips(7, seed=91)
+    x[0, :] = 0.0                                           # digital silence -> the 1e-12 floor everywhere
+    xt = dev(x)
+    engine.set_precision(prec)
+    try:
+        engine.frontend_config_contrib(480, 160, 16000, 20.0, 4000.0, 40, 40)
+        spec = engine.features(xt, "spec").cpu().numpy()
+        lm = engine.features(xt, "logmel").cpu().numpy()
+        mf = engine.features(xt, "mfcc").cpu().numpy()
+    finally:
+        engine.set_precision("fp32")
+        engine.frontend_config(480, 160, 40, 40)
+    r_pow = frontend.contrib_audio_spectrogram(x, 480, 160, magnitude_squared=True)
+    r_lm = frontend.contrib_mfcc(r_pow, return_log_mel=True)
+    r_mf = frontend.contrib_mfcc(r_pow)
+    assert spec.shape == r_pow.shape == (7, 98, 257) and mf.shape == r_mf.shape == (7, 98, 40)
+    assert rel_err(spec, r_pow) < 1e-5
+    assert np.array_equal(lm[0], r_lm[0]) and np.all(lm[0] == np.log(np.float32(1e-12)))
+    assert rel_err(lm[1:], r_lm[1:]) < 1e-4, rel_err(lm[1:], r_lm[1:])
+    assert rel_err(mf[1:], r_mf[1:]) < 1e-4, rel_err(mf[1:], r_mf[1:])
+    loud = np.exp(r_lm[1:]) > 1e-3
+    np.testing.assert_allclose(lm[1:][loud], r_lm[1:][loud], rtol=1e-4, atol=1e-4)
+
+
+def test_audio_converter_surface(engine):
+    from speech_recognition_b200.audio_converter import AudioConverter
+    x = synth.make_clips(3, seed=92)
+    conv = AudioConverter(engine=engine)
+    try:
+        got = conv.load_batch(x)
+        one = conv.load(x[1])
+    finally:
+        engine.frontend_config(480, 160, 40, 40)
+    ref = frontend.contrib_mfcc(frontend.contrib_audio_spectrogram(x))
+    assert got.shape == (3, 98, 40) and one.shape == (1, 98, 40)
+    assert rel_err(got, ref) < 1e-4 and np.array_equal(one[0], got[1])

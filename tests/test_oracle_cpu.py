@@ -179,3 +179,37 @@ def test_tta_predict_order():
     assert np.array_equal(calls[1], (np.float32(1.2) * x).astype(np.float32))     # loud
     assert np.array_equal(calls[2], np.roll(x, -1500, axis=1))                    # left
     assert np.array_equal(pred, [2, 2])
+
+
+def test_contrib_audio_restatement_properties():
+    """Native contrib_audio flavour (audio.py:15-23), parity unpinned: internal consistency checks of the
+    restatement -- the filterbank splits every in-band bin between two adjacent channels (weights sum to
+    one), the DCT equals scipy's DCT-II up to the sqrt(2/N)/2 normalisation of mfcc_dct.cc, and the power
+    spectrogram equals the squared tf.signal-style magnitude."""
+    from scipy.fft import dct
+    from oracle import frontend as fe
+    from speech_recognition_b200 import synth
+    band, w, start, end = fe.contrib_mel_filterbank(257, 16000.0, 40, 20.0, 4000.0)
+    assert (start, end) == (2, 128)
+    assert (band[:start] == -2).all() and (band[end + 1:] == -2).all()
+    assert (np.diff(band[start:end + 1]) >= 0).all() and band[start:end + 1].max() == 39
+    assert ((w[start:end + 1] >= 0) & (w[start:end + 1] <= 1)).all()
+    x = synth.make_clips(2, seed=5)
+    p = fe.contrib_audio_spectrogram(x)
+    m = fe.contrib_audio_spectrogram(x, magnitude_squared=False)
+    assert np.allclose(p, m.astype(np.float64) ** 2, rtol=1e-5, atol=1e-12)
+    # same frames / window as the tf.signal chain (window in double vs fp32: 1e-6 apart)
+    assert np.allclose(m, fe.spectrogram(x), rtol=1e-4, atol=1e-5)
+    lm = fe.contrib_mfcc(p, return_log_mel=True).astype(np.float64)
+    mf = fe.contrib_mfcc(p)
+    assert np.abs(dct(lm, type=2, axis=-1) * np.sqrt(2.0 / 40) / 2 - mf).max() < 1e-4
+    # a unit-magnitude flat spectrum puts (sum of weights) into each channel
+    flat = np.ones((1, 257), np.float32)
+    e = np.exp(fe.contrib_mfcc(flat, return_log_mel=True).astype(np.float64))[0]
+    dense = np.zeros((257, 40))
+    for i in range(start, end + 1):
+        if band[i] >= 0:
+            dense[i, band[i]] += w[i]
+        if band[i] + 1 < 40:
+            dense[i, band[i] + 1] += 1 - w[i]
+    assert np.allclose(e, dense.sum(0), rtol=1e-6)
