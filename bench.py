@@ -35,6 +35,8 @@ FLOP_BLOCKS = FLOP_PER_VIEW - FLOP_CONV1 - FLOP_HEAD
 FLOP_FRONTEND = 50.7e6                     # DFT-as-GEMM + mel + DCT per clip
 BYTES_AUGMENT = 192020                     # per clip
 ACT_BYTES_VIEW_FP16 = 286720 * 2 * 2       # 12 block outputs written + read once, fp16
+WORKLOAD = ("config3: augment + log-mel(40 mel, 30/10 ms) + exp-195 Depthwise1D forward x 8 TTA views + TTA mean "
+            "+ argmax; one step = one batch")
 
 
 def block_bytes_per_view(arch=195):
@@ -160,9 +162,10 @@ def run_reference(args):
         "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * 64 / best["value"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "config3: augment + log-mel(40) + exp-195 Depthwise1D forward x 8 TTA views, "
-                               "CPU restatement of the reference path (TF 1.4/Keras not installable here)",
-                   "batch": 64, "views": 8},
+        "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "views": 8, "job_clips": N_CLIPS_JOB,
+                   "reference_arm": "CPU restatement of the reference path (oracle/, torch-CPU fp32, all host threads; "
+                                    "TF 1.4 / Keras 2.1.2 are not installable here), bounded sample of the workload: "
+                                    "batches of 64 clips x 8 views"},
         "cpu_baseline": best,
         "e2e": {"value": best["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
@@ -295,8 +298,7 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16" if args.precision == "tc" else "f32", "data": "synthetic",
-            "config": {"workload": "config3: augment + log-mel(40 mel, 30/10 ms) + exp-195 Depthwise1D forward "
-                                   "x 8 TTA views + TTA mean + argmax; one step = one batch",
+            "config": {"workload": WORKLOAD,
                        "batch_per_gpu": B, "views": V, "job_clips": N_CLIPS_JOB,
                        "l2_policy": "inputs larger than L2 (batch x 64 KB = %.0f MB)" % (B * 64e3 / 1e6),
                        "precision": args.precision, "max_rows": args.max_rows,

@@ -11,11 +11,15 @@
 // per bin -- with two running accumulators per frame, then log(. + 1e-6) and, for MFCC, the
 // DCT-II against a shared-memory basis.  Neither the spectrogram nor the mel energies touch HBM.
 //
-// Roles (448 threads, 1 CTA / SM, static round-robin over 128-frame tiles):
-//   warps 0-3  epilogue : tcgen05.ld -> magnitude -> banded mel -> log -> (DCT) -> global
-//   warp  4    MMA      : one thread issues tcgen05.mma
-//   warp  5    B loader : cp.async.bulk of pre-swizzled basis blocks (hi / lo, 256 columns x 64 k)
-//   warps 6-13 A producers: implicit framing from the waveform (each sample is read from HBM once,
+// Roles (576 threads, 1 CTA / SM, static round-robin over 128-frame tiles):
+//   warps 0-7  epilogue : tcgen05.ld -> magnitude -> banded mel (linear sums to smem) | log -> (DCT) -> global.
+//                         The accumulator fills TMEM, so MMA and epilogue of a tile alternate and the epilogue
+//                         (256 bins x sqrt + 2 FMA per frame, latency-bound with one warp per scheduler) was 3/4
+//                         of the tile time: two warps per TMEM lane quarter now take 128 bins each; the two
+//                         mel filters that straddle bin 128 are summed from both halves in a fixed order.
+//   warp  8    MMA      : one thread issues tcgen05.mma
+//   warp  9    B loader : cp.async.bulk of pre-swizzled basis blocks (hi / lo, 256 columns x 64 k)
+//   warps 10-17 A producers: implicit framing from the waveform (each sample is read from HBM once,
 //                           the 3x frame overlap is served by L1/L2), hi/lo split, swizzled store
 // Bin 256 (Nyquist) has no mel weight for any upper edge below the Nyquist frequency; the
 // 'spectrogram' representation (all 257 bins) and exotic window sizes stay on the fp32 GEMM chain.
@@ -32,14 +36,14 @@ using namespace tc;
 
 namespace {
 
-constexpr int F_EPI_WARPS = 4;
-constexpr int F_MMA_WARP = 4;
-constexpr int F_LOAD_WARP = 5;
-constexpr int F_PROD_WARP0 = 6;
+constexpr int F_EPI_WARPS = 8;
+constexpr int F_MMA_WARP = 8;
+constexpr int F_LOAD_WARP = 9;
+constexpr int F_PROD_WARP0 = 10;
 constexpr int F_PROD_THREADS = 256;
-constexpr int F_THREADS = 32 * F_PROD_WARP0 + F_PROD_THREADS;     // 448
+constexpr int F_THREADS = 32 * F_PROD_WARP0 + F_PROD_THREADS;     // 576
 constexpr int F_A_STAGES = 2;                                      // stage = hi slab + lo slab (32 KB)
-constexpr int F_B_STAGES = 4;                                      // block = 256 columns x 64 k (32 KB)
+constexpr int F_B_STAGES = 4;                                      // max ring depth; block = 256 columns x 64 k (32 KB)
 constexpr int F_NH = 256;                                          // columns per MMA instruction
 constexpr int F_BINS = 256;                                        // bins on the tensor-core path
 constexpr int F_B_BLOCK = F_NH * ROW_BYTES;                        // 32 KB
@@ -55,17 +59,20 @@ struct DftParams {
   const float* dct;          // [n_mel][64] zero padded
   int frames, hop, win, n_mel, n_keep;
   int rows_total, num_tiles, num_kb, last_ksteps;
+  int b_stages;              // basis ring depth (2..4, what shared memory allows)
+  int m_split;               // mel filter that is open when bin 128 starts: filters m_split, m_split + 1 straddle the halves
   int floor_mode;            // 0: log(mel + 1e-6) (input_data.py:378); 1: log(max(mel, 1e-12)) (contrib_audio Mfcc)
 };
 
-struct FSmem { uint32_t a_off, b_off, tab_off, dct_off, bar_off, total; };
+struct FSmem { uint32_t a_off, b_off, tab_off, dct_off, part_off, bar_off, total; };
 
-__host__ __device__ inline FSmem f_smem(int n_mel, bool mfcc) {
+__host__ __device__ inline FSmem f_smem(int n_mel, bool mfcc, int b_stages) {
   FSmem s; uint32_t o = 0;
   s.a_off = o; o += F_A_STAGES * F_A_STAGE;
-  s.b_off = o; o += F_B_STAGES * F_B_BLOCK;
+  s.b_off = o; o += static_cast<uint32_t>(b_stages) * F_B_BLOCK;
   s.tab_off = o; o += F_BINS * 16;
   s.dct_off = o; o += mfcc ? static_cast<uint32_t>(n_mel) * F_DCT_LD * 4u : 0u;
+  s.part_off = o; o += static_cast<uint32_t>(n_mel + 2) * TILE_M * 4u;   // linear mel sums [n_mel][128 rows] + 2 overlap rows
   s.bar_off = o; o += (2 * F_A_STAGES + 2 * F_B_STAGES + 2) * 8 + 16;
   s.total = o + 1024;
   return s;
@@ -74,12 +81,14 @@ __host__ __device__ inline FSmem f_smem(int n_mel, bool mfcc) {
 template <bool MFCC, bool FLOOR>
 __global__ void __launch_bounds__(F_THREADS, 1) stft_mel_tc_kernel(const DftParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const FSmem lay = f_smem(p.n_mel, MFCC);
+  const FSmem lay = f_smem(p.n_mel, MFCC, p.b_stages);
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_base = smem + lay.a_off;
   uint8_t* b_base = smem + lay.b_off;
   float4* s_tab = reinterpret_cast<float4*>(smem + lay.tab_off);
   float* s_dct = reinterpret_cast<float*>(smem + lay.dct_off);
+  float* s_part = reinterpret_cast<float*>(smem + lay.part_off);  // [n_mel][128]
+  float* s_ovl = s_part + p.n_mel * TILE_M;                        // [2][128]: second half's share of filters m_split, m_split + 1
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_off);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + F_A_STAGES;
@@ -115,74 +124,86 @@ __global__ void __launch_bounds__(F_THREADS, 1) stft_mel_tc_kernel(const DftPara
     // =========================== epilogue ===========================
     uint32_t acc_phase = 0;
     const int out_dim = MFCC ? p.n_keep : p.n_mel;
+    const int q = warp & 3, hh = warp >> 2;                      // TMEM lane quarter; bin half [128 hh, 128 hh + 128)
+    const int row = q * 32 + lane;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       mbar_wait(acc_full, acc_phase);
       tc_fence_after();
-      const long long R = static_cast<long long>(tile) * TILE_M + warp * 32 + lane;
+      const long long R = static_cast<long long>(tile) * TILE_M + row;
       const bool ok = R < p.rows_total;
       float* orow = p.out + R * out_dim;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(hh * 256);
       float acc_a = 0.0f, acc_b = 0.0f;
-      int m_cur = 0;
-      float dctacc[MFCC ? F_DCT_LD : 1];
+      int m_cur = hh ? p.m_split : 0;
+      auto emit = [&]() {                                        // filter m_cur is complete for this half
+        if (m_cur < p.n_mel) {
+          float* dst = (hh && m_cur <= p.m_split + 1) ? s_ovl + (m_cur - p.m_split) * TILE_M : s_part + m_cur * TILE_M;
+          dst[row] = acc_a;
+        }
+        acc_a = acc_b; acc_b = 0.0f; ++m_cur;
+      };
+      auto bins16 = [&](const uint32_t (&v)[32], int bin0) {
 #pragma unroll
-      for (int k = 0; k < (MFCC ? F_DCT_LD : 1); ++k) dctacc[k] = 0.0f;
-      auto emit = [&]() {
-        const float lm = FLOOR ? logf(fmaxf(acc_a, 1e-12f)) : logf(acc_a + 1e-6f);   // TF mfcc.cc / input_data.py:378
-        if (MFCC) {
-          const float4* d4 = reinterpret_cast<const float4*>(s_dct + m_cur * F_DCT_LD);
+        for (int k = 0; k < 16; ++k) {
+          const float4 e = s_tab[bin0 + k];
+          for (int adv = __float_as_int(e.z); adv > 0; --adv) emit();      // warp-uniform
+          const float re = __uint_as_float(v[2 * k]), im = __uint_as_float(v[2 * k + 1]);
+          float mag;                                                         // ComplexAbs, input_data.py:366
+          asm("sqrt.approx.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(re, re, im * im)));   // MUFU.SQRT: 1 ulp-class, far inside the 1e-4 tier
+          acc_a = fmaf(mag, e.x, acc_a);
+          acc_b = fmaf(mag, e.y, acc_b);
+        }
+      };
+      {                                                          // next TMEM load in flight during the math
+        uint32_t va[32], vb[32];
+        tmem_ld32(taddr, va);
+        for (int c0 = 0; c0 < 256; c0 += 64) {
+          tmem_ld_wait();
+          tmem_ld32(taddr + c0 + 32, vb);
+          bins16(va, hh * 128 + c0 / 2);
+          tmem_ld_wait();
+          if (c0 + 64 < 256) tmem_ld32(taddr + c0 + 64, va);
+          bins16(vb, hh * 128 + c0 / 2 + 16);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty);                                    // TMEM is free for the next tile
+      acc_phase ^= 1;
+      if (hh == 0) { emit(); emit(); }                           // flush the two open filters m_split, m_split + 1
+      else while (m_cur < p.n_mel) emit();
+      asm volatile("bar.sync 1, %0;" ::"n"(F_EPI_WARPS * 32) : "memory");    // all linear mel sums of the tile are in smem
+      auto log_mel = [&](int m) {
+        float v = s_part[m * TILE_M + row];
+        if (m == p.m_split) v += s_ovl[row];
+        if (m == p.m_split + 1) v += s_ovl[TILE_M + row];
+        return FLOOR ? logf(fmaxf(v, 1e-12f)) : logf(v + 1e-6f);             // TF mfcc.cc / input_data.py:378
+      };
+      if (MFCC) {                                                // this thread: DCT outputs [32 hh, 32 hh + 32) of its row
+        float dctacc[F_DCT_LD / 2];
 #pragma unroll
-          for (int k = 0; k < F_DCT_LD / 4; ++k) {
+        for (int k = 0; k < F_DCT_LD / 2; ++k) dctacc[k] = 0.0f;
+        for (int m = 0; m < p.n_mel; ++m) {
+          const float lm = log_mel(m);
+          const float4* d4 = reinterpret_cast<const float4*>(s_dct + m * F_DCT_LD + hh * (F_DCT_LD / 2));
+#pragma unroll
+          for (int k = 0; k < F_DCT_LD / 8; ++k) {
             const float4 d = d4[k];
             dctacc[4 * k] = fmaf(lm, d.x, dctacc[4 * k]);
             dctacc[4 * k + 1] = fmaf(lm, d.y, dctacc[4 * k + 1]);
             dctacc[4 * k + 2] = fmaf(lm, d.z, dctacc[4 * k + 2]);
             dctacc[4 * k + 3] = fmaf(lm, d.w, dctacc[4 * k + 3]);
           }
-        } else if (ok) {
-          orow[m_cur] = lm;
         }
-        acc_a = acc_b; acc_b = 0.0f; ++m_cur;
-      };
-      auto bins16 = [&](const uint32_t (&v)[32], int bin0) {
+        if (ok) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const float4 e = s_tab[bin0 + q];
-          for (int adv = __float_as_int(e.z); adv > 0; --adv) emit();      // warp-uniform
-          const float re = __uint_as_float(v[2 * q]), im = __uint_as_float(v[2 * q + 1]);
-          const float mag = sqrtf(fmaf(re, re, im * im));                   // ComplexAbs, input_data.py:366
-          acc_a = fmaf(mag, e.x, acc_a);
-          acc_b = fmaf(mag, e.y, acc_b);
+          for (int k = 0; k < F_DCT_LD / 2; ++k)
+            if (hh * (F_DCT_LD / 2) + k < p.n_keep) orow[hh * (F_DCT_LD / 2) + k] = dctacc[k];
         }
-      };
-      if (MFCC) {                                                // 64 DCT accumulators: one TMEM buffer
-        uint32_t va[32];
-        for (int c0 = 0; c0 < 512; c0 += 32) {
-          tmem_ld32(taddr + c0, va);
-          tmem_ld_wait();
-          bins16(va, c0 / 2);
-        }
-      } else {                                                   // next TMEM load in flight during the math
-        uint32_t va[32], vb[32];
-        tmem_ld32(taddr, va);
-        for (int c0 = 0; c0 < 512; c0 += 64) {
-          tmem_ld_wait();
-          tmem_ld32(taddr + c0 + 32, vb);
-          bins16(va, c0 / 2);
-          tmem_ld_wait();
-          if (c0 + 64 < 512) tmem_ld32(taddr + c0 + 64, va);
-          bins16(vb, c0 / 2 + 16);
-        }
+      } else if (ok) {                                           // this thread: log-mel outputs of its half of the filters
+        const int m_half = (p.n_mel + 1) / 2;
+        for (int m = hh * m_half; m < min(p.n_mel, (hh + 1) * m_half); ++m) orow[m] = log_mel(m);
       }
-      tc_fence_before();
-      mbar_arrive(acc_empty);                                    // TMEM is free for the next tile
-      acc_phase ^= 1;
-      while (m_cur < p.n_mel) emit();
-      if (MFCC && ok) {
-#pragma unroll
-        for (int k = 0; k < F_DCT_LD; ++k)
-          if (k < p.n_keep) orow[k] = dctacc[k];
-      }
+      asm volatile("bar.sync 1, %0;" ::"n"(F_EPI_WARPS * 32) : "memory");    // smem sums may be overwritten
     }
   } else if (warp == F_MMA_WARP) {
     // =========================== MMA issuer ===========================
@@ -207,14 +228,14 @@ __global__ void __launch_bounds__(F_THREADS, 1) stft_mel_tc_kernel(const DftPara
             for (int ks = 0; ks < ksteps; ++ks)
               umma_f16(d, umma_desc_sw128(a_lo + ks * 32), umma_desc_sw128(b + ks * 32), idesc, 1u);
             umma_commit(&b_empty[sb]);
-            if (++sb == F_B_STAGES) { sb = 0; pb ^= 1; }
+            if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
             mbar_wait(&b_full[sb], pb);
             tc_fence_after();
             b = smem_u32(b_base + sb * F_B_BLOCK);
             for (int ks = 0; ks < ksteps; ++ks)
               umma_f16(d, umma_desc_sw128(a_hi + ks * 32), umma_desc_sw128(b + ks * 32), idesc, 1u);
             umma_commit(&b_empty[sb]);
-            if (++sb == F_B_STAGES) { sb = 0; pb ^= 1; }
+            if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
           }
           umma_commit(&a_empty[sa]);
           if (++sa == F_A_STAGES) { sa = 0; pa ^= 1; }
@@ -236,7 +257,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) stft_mel_tc_kernel(const DftPara
           uint8_t* dst = b_base + sb * F_B_BLOCK;
           bulk_g2s(dst, src, 16384, &b_full[sb]);
           bulk_g2s(dst + 16384, src + 16384, 16384, &b_full[sb]);
-          if (++sb == F_B_STAGES) { sb = 0; pb ^= 1; }
+          if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
         }
       }
     }
@@ -317,7 +338,9 @@ int frontend_build_tc(kws_handle* h, const float* basis, const float* mel, const
   // ---- banded mel: every bin feeds at most two adjacent filters (m, m+1), m non-decreasing ----
   std::vector<float> tab(static_cast<size_t>(F_BINS) * 4, 0.0f);
   int m_cur = 0;
+  fe.tc_m_split = 0;
   for (int j = 0; j < nb; ++j) {
+    if (j == F_BINS / 2) fe.tc_m_split = m_cur;                   // filter open when the second bin half starts
     int lo = -1, hi = -1;
     for (int m = 0; m < fe.n_mel; ++m)
       if (mel[static_cast<size_t>(j) * fe.n_mel + m] != 0.0f) { if (lo < 0) lo = m; hi = m; }
@@ -386,7 +409,10 @@ int launch_features_tc(kws_handle* h, const float* wav, int B, int kind, float* 
   p.num_kb = fe.tc_kblocks; p.last_ksteps = fe.tc_last_ksteps;
   p.floor_mode = fe.flavour == 1;
   const bool mfcc = kind == KWS_FEAT_MFCC;
-  const FSmem lay = f_smem(fe.n_mel, mfcc);
+  p.m_split = fe.tc_m_split;
+  p.b_stages = F_B_STAGES;
+  while (p.b_stages > 2 && static_cast<int>(f_smem(fe.n_mel, mfcc, p.b_stages).total) > F_SMEM_LIMIT) --p.b_stages;
+  const FSmem lay = f_smem(fe.n_mel, mfcc, p.b_stages);
   if (static_cast<int>(lay.total) > F_SMEM_LIMIT) return launch_features_f32(h, wav, B, kind, out, st);
   static bool attr_set = false;
   if (!attr_set) {
