@@ -382,8 +382,16 @@ int kws_pipeline_host(kws_t* h, int slot, const float* wav_h, const int32_t* shi
   }
   cudaStream_t st = h->own_stream, s_in = h->h2d_stream, s_out = h->d2h_stream;
   int k = 0;
-  for (int b0 = 0; b0 < B; b0 += chunk, ++k) {
-    const int nb = std::min(chunk, B - b0);
+  // The first and last chunks are shorter (1/4, 1/2 of a chunk): the first H2D copy and the last D2H copy
+  // are the only ones that cannot hide under kernels, so they are kept small.
+  const bool ramp = B >= 4 * chunk && chunk >= 64;
+  for (int b0 = 0, nb = 0; b0 < B; b0 += nb, ++k) {
+    nb = std::min(chunk, B - b0);
+    if (ramp) {
+      if (k == 0) nb = chunk / 4;
+      else if (k == 1) nb = chunk / 2;
+      else if (B - b0 > chunk / 4 && B - b0 <= chunk + chunk / 4) nb = B - b0 - chunk / 4;   // leave a short tail
+    }
     const int slot_k = k & 1;
     char* base = static_cast<char*>(h->stage_d) + slot_k * lay.total;
     float* d_wav = reinterpret_cast<float*>(base + lay.wav);

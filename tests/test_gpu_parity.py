@@ -393,3 +393,34 @@ def test_audio_converter_surface(engine):
     ref = frontend.contrib_mfcc(frontend.contrib_audio_spectrogram(x))
     assert got.shape == (3, 98, 40) and one.shape == (1, 98, 40)
     assert rel_err(got, ref) < 1e-4 and np.array_equal(one[0], got[1])
+
+
+def test_full_shard_size_chunk_independence(engine):
+    """Size-independent property at the full job's per-GPU share (158,538 clips / 8 GPUs = 19,818 clips x 8
+    TTA views): a clip's probabilities do not depend on where in the batch (which chunk, which tile, which CTA)
+    it sits -- the batch is 512 distinct clips tiled, so the output must be bit-periodic with period 512 --
+    through both the device entry point and the pipelined host entry point (ragged chunk ramp included)."""
+    from speech_recognition_b200 import Engine
+    eng = Engine(device=0, max_rows=8192, precision="tc")
+    try:
+        w = synth.synthetic_weights(195)
+        eng.load_model(0, 195, w)
+        eng.frontend_config(480, 160, 40, 40)
+        base = synth.make_clips(512, seed=1234)
+        B = 19818
+        reps = (B + 511) // 512
+        x = np.tile(base, (reps, 1))[:B]
+        probs, amax = eng.forward(dev(x), views=TTA_8)
+        probs = probs.cpu().numpy(); amax = amax.cpu().numpy()
+        assert probs.shape == (B, 12) and np.isfinite(probs).all()
+        np.testing.assert_allclose(probs.sum(1), 1.0, atol=1e-5)
+        ref_p, ref_a = probs[:512], amax[:512]
+        for s in range(512, B, 512):
+            n = min(512, B - s)
+            assert np.array_equal(probs[s:s + n], ref_p[:n]) and np.array_equal(amax[s:s + n], ref_a[:n]), s
+        hp, ha = eng.predict_host(x, views=TTA_8)
+        assert np.array_equal(hp, probs) and np.array_equal(ha, amax)
+        # argmax is the first maximum of the mean probabilities (make_submission.py:146)
+        assert np.array_equal(amax, probs.argmax(1).astype(np.int32))
+    finally:
+        eng.close()
