@@ -68,6 +68,20 @@ def tta_predict(predict, x: np.ndarray, views=TTA_SHIPPED):
     return probs, probs.argmax(axis=-1)
 
 
+def speed_tta_predict(predict, x: np.ndarray, x_slow: np.ndarray):
+    """make_submission.py:124-146 with use_speed_tta=True: six probability vectors summed in the
+    reference's order and divided by 10 (sic)."""
+    x = np.float32(x); x_slow = np.float32(x_slow)
+    probs = np.asarray(predict(x), np.float32)
+    left = np.asarray(predict(np.roll(x, -1500, axis=1)), np.float32)
+    loud = np.asarray(predict(np.float32(1.2) * x), np.float32)
+    slow = np.asarray(predict(x_slow), np.float32)
+    slow_loud = np.asarray(predict(np.clip(np.float32(1.1) * x_slow, -1.0, 1.0)), np.float32)
+    slow_silent = np.asarray(predict(np.float32(0.9) * x_slow), np.float32)
+    out = ((probs + loud + left + slow + slow_loud + slow_silent) / np.float32(10)).astype(np.float32)
+    return out, out.argmax(axis=-1)
+
+
 def class_map_32_to_12(order: str = "heng"):
     """For each of the 32 classes, the destination column in the 12-class vector.
     order='heng'  : convert_from_see_v3_bugfix.py:67,76-92 (AUDIO_NAMES order)

@@ -77,6 +77,7 @@ struct kws_handle {
   int max_rows = 0;
   int precision = KWS_PREC_TC;
   bool fuse_conv1_block1 = true;
+  uint32_t smem_attr_done = 0;            // per-handle (= per-device) bits: MaxDynamicSharedMemorySize set for kernel k
   int num_sms = kws::NUM_SMS_B200;
   std::string err;
   int64_t launches = 0;

@@ -35,12 +35,14 @@ __device__ __forceinline__ float warp_max(float v) {
 // memory for the whole launch -- re-fetching them per clip-view from L2 is what bounds a
 // one-CTA-per-clip formulation -- and every warp owns one (clip, view) at a time: lane-strided dot
 // products (bank-conflict-free: the row stride of dense_1 is 9 words), warp-shuffle reductions,
-// pooled features in registers.  A CTA iteration covers floor(16 / n_views) clips; the per-view
-// probabilities meet in shared memory and are averaged in view order.
+// pooled features in registers.  The stage is bound by shared-memory bandwidth (166 KB of dense_1
+// weights per clip-view), so a warp takes IPW consecutive views of one clip at a time and reuses
+// every weight it reads for all of them.  A CTA iteration covers floor(16 * IPW / n_views) clips;
+// the per-view probabilities meet in shared memory and are averaged in view order.
 constexpr int HEAD_WARPS = 16;
 constexpr int HEAD_CH_PER_LANE = 16;              // channels per lane in the pooling: C <= 512
 
-template <typename TAct>
+template <typename TAct, int IPW>
 __global__ void __launch_bounds__(HEAD_WARPS * 32, 1)
 head_kernel(const TAct* __restrict__ act, int C, int n_views, int n_clips, const float* __restrict__ w_d1,
             const float* __restrict__ b_d1, const float* __restrict__ w_d2, int classes,
@@ -50,7 +52,7 @@ head_kernel(const TAct* __restrict__ act, int C, int n_views, int n_clips, const
   const int feat = pool_max_avg ? 2 * C : C;
   float* w1 = sm;                                       // [n][HEAD_T]
   float* w2t = w1 + n * HEAD_T;                         // [classes][feat]
-  float* pv = w2t + classes * feat;                     // [HEAD_WARPS][32] per-view probabilities
+  float* pv = w2t + classes * feat;                     // [clips per iteration][n_views][32] per-view probabilities
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   {
@@ -65,80 +67,94 @@ head_kernel(const TAct* __restrict__ act, int C, int n_views, int n_clips, const
   const float bias = lane < HEAD_T ? __ldg(&b_d1[lane]) : 0.0f;
   __syncthreads();
 
-  const int cpi = HEAD_WARPS / n_views;                 // clips per CTA iteration (n_views <= 16)
-  const int ci = warp / n_views, v = warp - ci * n_views;
+  const int wpc = n_views / IPW;                        // warps per clip (IPW divides n_views)
+  const int cpi = HEAD_WARPS / wpc;                     // clips per CTA iteration
+  const int ci = warp / wpc, v0 = (warp - ci * wpc) * IPW;
   for (int clip0 = blockIdx.x * cpi; clip0 < n_clips; clip0 += gridDim.x * cpi) {
     const int clip = clip0 + ci;
     if (ci < cpi && clip < n_clips) {
-      const TAct* x = act + (static_cast<size_t>(clip) * n_views + v) * n;
-      // ---- dense_1 + softmax over T ----
-      float p[HEAD_T];
+      const TAct* x0 = act + (static_cast<size_t>(clip) * n_views + v0) * n;
+      // ---- dense_1 of IPW views against the same weights ----
+      float p[IPW][HEAD_T];
 #pragma unroll
-      for (int j = 0; j < HEAD_T; ++j) p[j] = 0.0f;
-#pragma unroll 16                                        // 16 activation loads in flight per lane (latency-bound otherwise)
+      for (int u = 0; u < IPW; ++u)
+#pragma unroll
+        for (int j = 0; j < HEAD_T; ++j) p[u][j] = 0.0f;
+#pragma unroll 8                                         // 8 x IPW activation loads in flight per lane
       for (int i = lane; i < n; i += 32) {
-        const float xv = to_float(x[i]);
+        float xv[IPW];
+#pragma unroll
+        for (int u = 0; u < IPW; ++u) xv[u] = to_float(x0[static_cast<size_t>(u) * n + i]);
         const float* wr = w1 + i * HEAD_T;
 #pragma unroll
-        for (int j = 0; j < HEAD_T; ++j) p[j] = fmaf(xv, wr[j], p[j]);
-      }
-      float l = -INFINITY;
+        for (int j = 0; j < HEAD_T; ++j) {
+          const float w = wr[j];
 #pragma unroll
-      for (int j = 0; j < HEAD_T; ++j) {
-        const float s = warp_sum(p[j]);
-        if (lane == j) l = s + bias;
-      }
-      float mx = warp_max(l);
-      float e = lane < HEAD_T ? expf(l - mx) : 0.0f;
-      float s = warp_sum(e);
-      const float a = __fdiv_rn(e, s);                   // lane t holds att[t]
-      float att[HEAD_T];
-#pragma unroll
-      for (int t = 0; t < HEAD_T; ++t) att[t] = __shfl_sync(0xffffffffu, a, t);
-      // ---- multiply_1 + pooling: lane owns channels lane, lane + 32, ... ----
-      float z0[HEAD_CH_PER_LANE], z1[HEAD_CH_PER_LANE];
-#pragma unroll
-      for (int k = 0; k < HEAD_CH_PER_LANE; ++k) {
-        const int c = lane + 32 * k;
-        z0[k] = 0.0f; z1[k] = 0.0f;
-        if (c < C) {
-          float m = -INFINITY, sum_x = 0.0f, sum_w = 0.0f;
-#pragma unroll
-          for (int t = 0; t < HEAD_T; ++t) {
-            const float xv = to_float(x[t * C + c]);
-            const float wv = __fmul_rn(xv, att[t]);          // multiply_1
-            m = fmaxf(m, wv);
-            sum_x += xv;
-            sum_w += wv;
-          }
-          if (pool_max_avg) {
-            z0[k] = m;                                       // global_max_pooling1d_1(x * a)
-            z1[k] = __fdiv_rn(sum_x, static_cast<float>(HEAD_T));   // global_average_pooling1d_1(x)
-          } else {
-            z0[k] = __fdiv_rn(sum_w, static_cast<float>(HEAD_T));   // exp 106: mean_t(x * a)
-          }
+          for (int u = 0; u < IPW; ++u) p[u][j] = fmaf(xv[u], w, p[u][j]);
         }
       }
-      // ---- dense_2 + softmax ----
-      l = -INFINITY;
-      for (int j = 0; j < classes; ++j) {
-        const float* wc = w2t + j * feat;
-        float d = 0.0f;
+#pragma unroll
+      for (int u = 0; u < IPW; ++u) {
+        const TAct* x = x0 + static_cast<size_t>(u) * n;
+        // ---- softmax over T ----
+        float l = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < HEAD_T; ++j) {
+          const float s = warp_sum(p[u][j]);
+          if (lane == j) l = s + bias;
+        }
+        float mx = warp_max(l);
+        float e = lane < HEAD_T ? expf(l - mx) : 0.0f;
+        float s = warp_sum(e);
+        const float a = __fdiv_rn(e, s);                   // lane t holds att[t]
+        float att[HEAD_T];
+#pragma unroll
+        for (int t = 0; t < HEAD_T; ++t) att[t] = __shfl_sync(0xffffffffu, a, t);
+        // ---- multiply_1 + pooling: lane owns channels lane, lane + 32, ... ----
+        float z0[HEAD_CH_PER_LANE], z1[HEAD_CH_PER_LANE];
 #pragma unroll
         for (int k = 0; k < HEAD_CH_PER_LANE; ++k) {
           const int c = lane + 32 * k;
+          z0[k] = 0.0f; z1[k] = 0.0f;
           if (c < C) {
-            d = fmaf(z0[k], wc[c], d);
-            if (pool_max_avg) d = fmaf(z1[k], wc[C + c], d);
+            float m = -INFINITY, sum_x = 0.0f, sum_w = 0.0f;
+#pragma unroll
+            for (int t = 0; t < HEAD_T; ++t) {
+              const float xv = to_float(x[t * C + c]);
+              const float wv = __fmul_rn(xv, att[t]);          // multiply_1
+              m = fmaxf(m, wv);
+              sum_x += xv;
+              sum_w += wv;
+            }
+            if (pool_max_avg) {
+              z0[k] = m;                                       // global_max_pooling1d_1(x * a)
+              z1[k] = __fdiv_rn(sum_x, static_cast<float>(HEAD_T));   // global_average_pooling1d_1(x)
+            } else {
+              z0[k] = __fdiv_rn(sum_w, static_cast<float>(HEAD_T));   // exp 106: mean_t(x * a)
+            }
           }
         }
-        d = warp_sum(d);
-        if (lane == j) l = d;
+        // ---- dense_2 + softmax ----
+        l = -INFINITY;
+        for (int j = 0; j < classes; ++j) {
+          const float* wc = w2t + j * feat;
+          float d = 0.0f;
+#pragma unroll
+          for (int k = 0; k < HEAD_CH_PER_LANE; ++k) {
+            const int c = lane + 32 * k;
+            if (c < C) {
+              d = fmaf(z0[k], wc[c], d);
+              if (pool_max_avg) d = fmaf(z1[k], wc[C + c], d);
+            }
+          }
+          d = warp_sum(d);
+          if (lane == j) l = d;
+        }
+        mx = warp_max(l);
+        e = lane < classes ? expf(l - mx) : 0.0f;
+        s = warp_sum(e);
+        pv[(ci * n_views + v0 + u) * 32 + lane] = __fdiv_rn(e, s);
       }
-      mx = warp_max(l);
-      e = lane < classes ? expf(l - mx) : 0.0f;
-      s = warp_sum(e);
-      pv[warp * 32 + lane] = __fdiv_rn(e, s);
     }
     __syncthreads();
     if (warp < cpi && clip0 + warp < n_clips) {           // warp w averages the views of clip clip0 + w
@@ -191,28 +207,33 @@ int launch_head(kws_handle* h, Model& m, const void* act, bool act_half, int n_c
   const int C = m.c_last;
   if (C > 32 * HEAD_CH_PER_LANE || C % 4) return fail(h, KWS_EUNSUPPORTED, "head expects at most 512 channels");
   const int feat = m.pool_max_avg ? 2 * C : C;
+  const int ipw = n_views % 4 == 0 ? 4 : (n_views % 2 == 0 ? 2 : 1);   // views per warp (weights reused from registers)
+  const int cpi = HEAD_WARPS / (n_views / ipw);
   const size_t smem = (static_cast<size_t>(HEAD_T) * C * HEAD_T + static_cast<size_t>(m.classes) * feat +
-                       HEAD_WARPS * 32) * sizeof(float);
+                       static_cast<size_t>(cpi) * n_views * 32) * sizeof(float);
   if (smem > 227 * 1024) return fail(h, KWS_EUNSUPPORTED, "head weights do not fit in shared memory");
-  static bool attr_set = false;
-  if (!attr_set) {
-    KWS_CUDA(h, cudaFuncSetAttribute(head_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    KWS_CUDA(h, cudaFuncSetAttribute(head_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  const int cpi = HEAD_WARPS / n_views;
   const int grid = std::max(1, std::min(h->num_sms, (n_clips + cpi - 1) / cpi));
-  KWS_T0(h, KC_HEAD, st);
+  const int pm = m.pool_max_avg ? 1 : 0;
+  const uint32_t attr_bit = 32u << ((act_half ? 0 : 3) + (ipw == 4 ? 2 : ipw == 2 ? 1 : 0));
+  auto launch = [&](auto kern, auto* a) -> int {
+    if (!(h->smem_attr_done & attr_bit)) {
+      KWS_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      h->smem_attr_done |= attr_bit;
+    }
+    KWS_T0(h, KC_HEAD, st);
+    kern<<<grid, HEAD_WARPS * 32, smem, st>>>(a, C, n_views, n_clips, m.w_d1, m.b_d1, m.w_d2, m.classes, pm, probs_mean, argmax);
+    KWS_T1(h, st);
+    return KWS_OK;
+  };
+  int rc;
   if (act_half) {
-    head_kernel<__half><<<grid, HEAD_WARPS * 32, smem, st>>>(
-        static_cast<const __half*>(act), C, n_views, n_clips, m.w_d1, m.b_d1, m.w_d2, m.classes,
-        m.pool_max_avg ? 1 : 0, probs_mean, argmax);
+    const __half* a = static_cast<const __half*>(act);
+    rc = ipw == 4 ? launch(head_kernel<__half, 4>, a) : ipw == 2 ? launch(head_kernel<__half, 2>, a) : launch(head_kernel<__half, 1>, a);
   } else {
-    head_kernel<float><<<grid, HEAD_WARPS * 32, smem, st>>>(
-        static_cast<const float*>(act), C, n_views, n_clips, m.w_d1, m.b_d1, m.w_d2, m.classes,
-        m.pool_max_avg ? 1 : 0, probs_mean, argmax);
+    const float* a = static_cast<const float*>(act);
+    rc = ipw == 4 ? launch(head_kernel<float, 4>, a) : ipw == 2 ? launch(head_kernel<float, 2>, a) : launch(head_kernel<float, 1>, a);
   }
-  KWS_T1(h, st);
+  if (rc) return rc;
   KWS_LAUNCH_CHECK(h);
   return KWS_OK;
 }

@@ -414,13 +414,12 @@ int launch_features_tc(kws_handle* h, const float* wav, int B, int kind, float* 
   while (p.b_stages > 2 && static_cast<int>(f_smem(fe.n_mel, mfcc, p.b_stages).total) > F_SMEM_LIMIT) --p.b_stages;
   const FSmem lay = f_smem(fe.n_mel, mfcc, p.b_stages);
   if (static_cast<int>(lay.total) > F_SMEM_LIMIT) return launch_features_f32(h, wav, B, kind, out, st);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!(h->smem_attr_done & 1u)) {
     KWS_CUDA(h, cudaFuncSetAttribute(stft_mel_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_LIMIT));
     KWS_CUDA(h, cudaFuncSetAttribute(stft_mel_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_LIMIT));
     KWS_CUDA(h, cudaFuncSetAttribute(stft_mel_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_LIMIT));
     KWS_CUDA(h, cudaFuncSetAttribute(stft_mel_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_LIMIT));
-    attr_set = true;
+    h->smem_attr_done |= 1u;
   }
   const int grid = std::min(p.num_tiles, h->num_sms);
   KWS_T0(h, KC_DFT, st);

@@ -1106,10 +1106,9 @@ int launch_tc_gemm(kws_handle* h, GemmParams& p, cudaStream_t st) {
   }
   if (!chosen) return fail(h, KWS_EUNSUPPORTED, "layer does not fit in shared memory");
   const SmemLayout lay = smem_layout(p, conv1);
-  static bool attr_set[3] = {false, false, false};
-  if (!attr_set[MODE]) {
+  if (!(h->smem_attr_done & (2u << MODE))) {
     KWS_CUDA(h, cudaFuncSetAttribute(tc_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_set[MODE] = true;
+    h->smem_attr_done |= 2u << MODE;
   }
   const int grid = std::min(p.num_tiles, h->num_sms / p.n_split) * p.n_split;
   if (grid <= 0) return KWS_OK;
@@ -1150,10 +1149,9 @@ int launch_conv1_block1(kws_handle* h, Model& m, const float* wav, int nb, const
   if (rc) return rc;
   const FusedSmem lay = fused_smem(p.c0, p.c1);
   if (static_cast<int>(lay.total) > SMEM_LIMIT) return fail(h, KWS_EUNSUPPORTED, "fused conv1d_1 + block 1 does not fit in shared memory");
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!(h->smem_attr_done & 16u)) {
     KWS_CUDA(h, cudaFuncSetAttribute(conv1_block1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_set = true;
+    h->smem_attr_done |= 16u;
   }
   const int grid = std::min(p.num_units, h->num_sms);
   if (grid <= 0) return KWS_OK;

@@ -41,6 +41,27 @@ class Model:
         return self.engine.predict_host(x, views=views, slot=self.slot)
 
 
+    def predict_speed_tta(self, x, x_slow):
+        """make_submission.py:124-146 with ``use_speed_tta``: x_slow holds the time-stretched copies that
+        create_tta_set.py wrote (librosa, offline).  Views: x, roll(x, -1500), 1.2 x, x_slow,
+        clip(1.1 x_slow, -1, 1), 0.9 x_slow; the reference divides the SIX probability vectors by 10
+        (sic, :140) -- kept, it does not change the argmax.  Returns (probs f32 [N,C], argmax int32 [N])."""
+        import torch
+        eng = self.engine
+        dev = f"cuda:{eng.device}"
+        xt = torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(dev)
+        st = torch.from_numpy(np.ascontiguousarray(x_slow, np.float32)).to(dev)
+        n = xt.shape[0]
+        p_a, _ = eng.forward(xt, views=TTA_SHIPPED, slot=self.slot)                 # mean of 3
+        p_b, _ = eng.forward(st, views=((0, 1.0), (0, 0.9)), slot=self.slot)        # mean of 2
+        zeros_i = torch.zeros((n,), dtype=torch.int32, device=dev)
+        loud = eng.augment(st, zeros_i, zeros_i - 1, zeros_i, torch.zeros((n,), dtype=torch.float32, device=dev),
+                           torch.full((n,), 1.1, dtype=torch.float32, device=dev), clamp=True)   # clip(1.1 x, -1, 1)
+        p_c, _ = eng.forward(loud, views=((0, 1.0),), slot=self.slot)
+        probs = (p_a * 3.0 + p_b * 2.0 + p_c) / 10.0
+        return probs.cpu().numpy(), probs.argmax(dim=1).to(torch.int32).cpu().numpy()
+
+
 def load_model(filepath, custom_objects=None, engine: Engine | None = None, slot: int = 0, **kw):
     """keras.models.load_model stand-in: .npz / Keras .hdf5 / frozen .pb -> Model.
     ``custom_objects`` is accepted and ignored (relu6, DepthwiseConv2D, ... are built in)."""

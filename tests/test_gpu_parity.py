@@ -424,3 +424,18 @@ def test_full_shard_size_chunk_independence(engine):
         assert np.array_equal(amax, probs.argmax(1).astype(np.int32))
     finally:
         eng.close()
+
+
+def test_speed_tta_driver(engine):
+    """use_speed_tta branch of make_submission.py:131-140 (six views / 10, one of them clipped to [-1, 1])."""
+    from speech_recognition_b200 import Model
+    w = synth.synthetic_weights(195)
+    m = Model(195, w, engine=engine, slot=1)
+    x = synth.make_clips(20, seed=501)
+    x_slow = np.roll(synth.make_clips(20, seed=502), 300, axis=1) * np.float32(1.6)   # stands in for the stretched set; clips at 1.1x
+    assert (np.abs(1.1 * x_slow) > 1.0).any()
+    probs, amax = m.predict_speed_tta(x, x_slow)
+    r_probs, r_amax = driver.speed_tta_predict(lambda v: network.forward(v, w, 195, dtype=torch.float64), x, x_slow)
+    assert np.abs(probs - r_probs).max() < 1e-4                  # engine fixture runs the fp32 tier
+    assert np.abs(probs.sum(1) - 0.6).max() < 1e-5               # six distributions over ten
+    assert np.array_equal(amax, r_amax)
