@@ -344,7 +344,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="clips per GPU per step")
-    ap.add_argument("--max-rows", type=int, default=8192, help="clip-views per internal chunk")
+    ap.add_argument("--max-rows", type=int, default=32768, help="clip-views per internal chunk")
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

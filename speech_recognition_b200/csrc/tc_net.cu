@@ -802,10 +802,13 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
       mbar_wait(&acc1_full[s1], static_cast<uint32_t>(i >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(s1 * p.c0 + ch0 * 8);
+      // the last tile of a clip-view holds 21 conv1d_1 rows / 19 block-1 rows: quarters and runs past them are skipped
+      const bool pack_on = q * 32 < p.t1 - j * FUSE_ROWS;
+      const bool fir_on = fkb < nkb2 && 8 * fg < p.t2 - j * FUSE_ROWS;
       for (int mem = p.vg.start[g]; mem < p.vg.start[g + 1]; ++mem, ++n2) {
         const float gain = p.vg.gain[mem];
         // ---- pack: this row's half of relu6(bn(gain * conv1d_1)) as fp16 into the row buffer ----
-        {
+        if (pack_on) {
           uint32_t va[32];
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
@@ -824,7 +827,7 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
         asm volatile("bar.sync 2, %0;" ::"n"(FUSE_MID_WARPS * 32) : "memory");   // all rows of this view are in the buffer
         mbar_wait(a2_empty, (static_cast<uint32_t>(n2) & 1u) ^ 1u);
         // ---- depthwise FIR: rows 8 fg .. 8 fg + 7 of chunk fc of K slab fkb (rows 126, 127 are never stored) ----
-        if (fkb < nkb2) {
+        if (fir_on) {
           const uint8_t* rsl = raw_base + fkb * A_SLAB_BYTES + (8 * fg) * ROW_BYTES;
           const int cg = fkb * 8 + fc;
           const uint4 k0 = *reinterpret_cast<const uint4*>(s_taps + cg * 8);
