@@ -7,7 +7,9 @@
 Workload (config.workload): BASELINE.json configs[2] = exp-195 Depthwise1D forward with 8x TTA, with
 the north-star stages in front of it -- one "step" is one pass over a batch of B synthetic 1 s / 16 kHz
 clips: augment (time-shift + noise mix + volumes) -> log-mel (40 mel, 30 ms / 10 ms) -> 8-view forward
--> TTA mean -> argmax.  B clips x 64 KB = 268 MB at the default B=4096, larger than the 126 MB L2.
+-> TTA mean -> argmax.  B clips x 64 KB = 1.05 GB at the default B=16384 (about the per-GPU share of
+the 158,538-clip job on 8 GPUs), far larger than the 126 MB L2; the forward runs in chunks of
+--max-rows clip-views (32768 = 4096 clips).
 Per-GPU work is fixed as N grows (weak scaling); the only collective is one all-gather of the
 [B,12] probabilities per step.  `value` times the device-resident path with CUDA events on the
 launching stream (max over ranks); `e2e` times the host-buffer C-ABI call (pinned host memory,
@@ -343,7 +345,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4096, help="clips per GPU per step")
+    ap.add_argument("--batch", type=int, default=16384, help="clips per GPU per step")
     ap.add_argument("--max-rows", type=int, default=32768, help="clip-views per internal chunk")
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
