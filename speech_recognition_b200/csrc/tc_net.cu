@@ -1075,6 +1075,16 @@ int launch_tc_gemm(kws_handle* h, GemmParams& p, cudaStream_t st) {
         const int b_stream = std::max(2, std::min(4, 65536 / b_block));
         if (ob_lo == 2) {                                        // narrow layers: deep A ring first
           p.out_bufs = 2;
+          static const int res_first = [] { const char* e = getenv("KWS_RES_FIRST"); return e ? atoi(e) : 0; }();   // A/B aid
+          if (res_first) {
+            for (int res = 1; res >= (resident_only ? 1 : 0) && !chosen; --res) {
+              if (res && blocks > MAX_B_BLOCKS) continue;
+              for (int a = 4; a >= 2 && !chosen; a -= 2)
+                for (int bs = res ? blocks : b_stream; bs >= (res ? blocks : 2) && !chosen; --bs)
+                  for (int r = 6; r >= r_min && !chosen; r -= 2)
+                    if (fits(a, bs, r)) { p.b_resident = res; chosen = true; }
+            }
+          }
           for (int a = 4; a >= 2 && !chosen; a -= 2)
             for (int res = 1; res >= (resident_only ? 1 : 0) && !chosen; --res) {
               if (res && blocks > MAX_B_BLOCKS) continue;

@@ -14,12 +14,18 @@ want = [("us", "gpu__time_duration.sum"), ("rdMB", "dram__bytes_read.sum"), ("wr
 ki = hdr.index("Kernel Name")
 print("| # | kernel | " + " | ".join(w[0] for w in want) + " |")
 print("|---|---|" + "---|" * len(want))
+units = rows[1]
+SCALE = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6,                      # -> us
+         "byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}        # -> MB
 for n, r in enumerate(rows[2:]):
     name = r[ki].split("::")[-1].split("(")[0][:28]
+    if name.startswith("GemmParams") or name.startswith("DftParams") or name.startswith("FusedParams"):
+        name = r[ki].split("(")[0].split("::")[-1][:28]
     vals = []
     for _, m in want:
         try:
-            vals.append("%.4g" % float(r[hdr.index(m)].replace(",", "")))
+            i = hdr.index(m)
+            vals.append("%.4g" % (float(r[i].replace(",", "")) * SCALE.get(units[i], 1.0)))
         except Exception:
             vals.append("-")
     print(f"| {n} | {name} | " + " | ".join(vals) + " |")
