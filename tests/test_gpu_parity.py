@@ -439,3 +439,42 @@ def test_speed_tta_driver(engine):
     assert np.abs(probs - r_probs).max() < 1e-4                  # engine fixture runs the fp32 tier
     assert np.abs(probs.sum(1) - 0.6).max() < 1e-5               # six distributions over ten
     assert np.array_equal(amax, r_amax)
+
+
+def test_config4_and_config5_pipelines(engine):
+    """BASELINE configs 4 and 5 end to end on the device (fp32 tier so labels are exact):
+    config 4 = exp-106 net -> 32->12 map + re-softmax + uint8 -> threshold 0.6 (REPR_106_pseudo /
+    create_pseudo_with_thresh); config 5 = 106 + 195 + 206, per-model TTA mean, 3-way vote with
+    min_count 2 and model-0 fallback (majority_vote.py:26-56) -- against the oracle's driver arithmetic."""
+    x = synth.make_clips(40, seed=610)
+    xt = dev(x)
+    w = {a: synth.synthetic_weights(a) for a in (106, 195, 206)}
+    for slot, a in enumerate((106, 195, 206)):
+        engine.load_model(slot, a, w[a])
+    # ---- config 4 ----
+    p32, _ = engine.forward(xt, views=TTA_SHIPPED, slot=0)
+    see, u8 = engine.convert_classes(p32, class_map_32_to_12("heng"), 12)
+    label, keep = engine.select(u8, 0.6)
+    r_p32, _ = driver.tta_predict(lambda v: network.forward(v, w[106], 106, dtype=torch.float64), x, TTA_SHIPPED)
+    assert np.abs(p32.cpu().numpy() - r_p32).max() < 1e-4
+    r_see, r_u8 = driver.convert_32_to_12(p32.cpu().numpy(), "heng")          # same inputs: integer path must be exact
+    d = np.abs(u8.cpu().numpy().astype(int) - r_u8.astype(int))
+    assert d.max() <= 1
+    r_label, r_keep = driver.threshold_select(u8.cpu().numpy(), 0.6)
+    assert np.array_equal(label.cpu().numpy(), r_label) and np.array_equal(keep.cpu().numpy().astype(bool), r_keep)
+    # ---- config 5 ----
+    cm = np.asarray(class_map_32_to_12("frozen"))                              # 32 -> 12 in the exp-195 class order
+    labels = []
+    for slot, a in enumerate((106, 195, 206)):
+        pr, am = engine.forward(xt, views=TTA_SHIPPED, slot=slot)
+        r_pr, r_am = driver.tta_predict(lambda v: network.forward(v, w[a], a, dtype=torch.float64), x, TTA_SHIPPED)
+        assert np.array_equal(am.cpu().numpy(), r_am), a
+        lab = am.cpu().numpy()
+        labels.append(cm[lab] if a == 106 else lab)
+    labels = np.stack(labels).astype(np.int32)
+    voted, clear = engine.vote(dev(labels), 2)
+    r_voted, r_clear = driver.majority_vote(labels, 2)
+    assert np.array_equal(voted.cpu().numpy(), r_voted) and np.array_equal(clear.cpu().numpy().astype(bool), r_clear)
+    # fallback rule: where all three disagree the first model's label is kept
+    alldiff = (labels[0] != labels[1]) & (labels[0] != labels[2]) & (labels[1] != labels[2])
+    assert np.array_equal(voted.cpu().numpy()[alldiff], labels[0][alldiff])
