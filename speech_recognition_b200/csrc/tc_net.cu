@@ -89,6 +89,9 @@ struct alignas(64) GemmParams {
   int n_views;              // one epilogue pass per member view (the gain is applied to the accumulator)
   // dw_pw A side
   const __half* dw_h;       // depthwise taps [3][cin] fp16
+  const __half* in_act;     // the previous activation itself (L2 prefetch of the rows of tiles ahead)
+  long long rows_in;
+  int prefetch_tiles;       // how many of this CTA's tiles ahead the raw loader prefetches into L2 (0 = off)
   // B side: pre-swizzled fp16 blocks of n_inst rows x 128 B, block j = (kb, nh) = (j / n_halves, j % n_halves)
   const uint8_t* w_img;
   // epilogue
@@ -488,52 +491,59 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
     if (lane == 0) bulk_wait_group_all();
   } else if (warp == MMA_WARP) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // all 32 lanes walk the loop (uniform control flow and registers); one elected lane issues
+    {
       const uint32_t idesc = umma_idesc_f16(TILE_M, p.n_inst, /*fp16*/ 0);
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(a_base)), b_lo0 = umma_desc_lo(smem_u32(b_base));
+      const uint32_t a_stage_lo = static_cast<uint32_t>(p.a_stage_bytes) >> 4, b_block_lo = b_block_bytes >> 4;
+      const int num_kb = p.num_kb, n_halves = p.n_halves, last_ksteps = p.last_ksteps;
+      const bool resident = p.b_resident != 0;
       int sa = 0; uint32_t pa = 0; int sb = 0; uint32_t pb = 0; int acc = 0; uint32_t acc_phase = 0;
+      if (resident && tile0 < p.num_tiles) {                     // the weights arrive once per launch
+        for (int j = 0; j < blocks_per_tile; ++j) mbar_wait(&b_full[j], 0);
+      }
       for (int tile = tile0; tile < p.num_tiles; tile += tstride) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d0 = tmem_base + static_cast<uint32_t>(acc * p.ncta);
         if (kConv1) mbar_wait(&a_full[sa], pa);                  // one stage = both slabs of the tile
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          uint32_t a_addr;
-          if (kConv1) {
-            a_addr = smem_u32(a_base + sa * p.a_stage_bytes + kb * A_SLAB_BYTES);
-          } else {
-            mbar_wait(&a_full[sa], pa);
-            a_addr = smem_u32(a_base + sa * p.a_stage_bytes);
-          }
-          const int ksteps = (kb == p.num_kb - 1) ? p.last_ksteps : 4;
-          for (int nh = 0; nh < p.n_halves; ++nh) {
-            uint32_t b_addr;
-            if (p.b_resident) {
-              const int j = kb * p.n_halves + nh;
-              mbar_wait(&b_full[j], 0);
-              b_addr = smem_u32(b_base + j * b_block_bytes);
-            } else {
+        uint32_t b_lo = b_lo0;                                   // resident: block j = (kb, nh) in order
+        for (int kb = 0; kb < num_kb; ++kb) {
+          uint32_t a_lo = a_lo0 + static_cast<uint32_t>(sa) * a_stage_lo;
+          if (kConv1) a_lo += static_cast<uint32_t>(kb) * (A_SLAB_BYTES >> 4);
+          else mbar_wait(&a_full[sa], pa);
+          const int ksteps = (kb == num_kb - 1) ? last_ksteps : 4;
+          for (int nh = 0; nh < n_halves; ++nh) {
+            if (!resident) {
               mbar_wait(&b_full[sb], pb);
-              b_addr = smem_u32(b_base + sb * b_block_bytes);
+              b_lo = b_lo0 + static_cast<uint32_t>(sb) * b_block_lo;
             }
             tc_fence_after();
-            for (int ks = 0; ks < ksteps; ++ks)
-              umma_f16(d0 + nh * p.n_inst, umma_desc_sw128(a_addr + ks * 32), umma_desc_sw128(b_addr + ks * 32),
-                       idesc, (kb | ks) != 0 ? 1u : 0u);
-            if (!p.b_resident) {
-              umma_commit(&b_empty[sb]);
-              if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+            if (elect_one()) {
+              const uint32_t d = d0 + static_cast<uint32_t>(nh * p.n_inst);
+              umma_f16_lo(d, a_lo, b_lo, idesc, kb != 0 ? 1u : 0u);
+              if (ksteps == 4) {
+                umma_f16_lo(d, a_lo + 2, b_lo + 2, idesc, 1u);
+                umma_f16_lo(d, a_lo + 4, b_lo + 4, idesc, 1u);
+                umma_f16_lo(d, a_lo + 6, b_lo + 6, idesc, 1u);
+              } else {
+                for (int ks = 1; ks < ksteps; ++ks) umma_f16_lo(d, a_lo + 2 * ks, b_lo + 2 * ks, idesc, 1u);
+              }
+              if (!resident) umma_commit(&b_empty[sb]);
+              if (!kConv1 && nh == n_halves - 1) umma_commit(&a_empty[sa]);
             }
+            __syncwarp();
+            if (!resident) { if (++sb == p.b_stages) { sb = 0; pb ^= 1; } }
+            else b_lo += b_block_lo;
           }
-          if (!kConv1) {
-            umma_commit(&a_empty[sa]);
-            if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
-          }
+          if (!kConv1) { if (++sa == p.a_stages) { sa = 0; pa ^= 1; } }
         }
-        if (kConv1) {
-          umma_commit(&a_empty[sa]);
-          if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+        if (elect_one()) {
+          if (kConv1) umma_commit(&a_empty[sa]);
+          umma_commit(&acc_full[acc]);
         }
-        umma_commit(&acc_full[acc]);
+        __syncwarp();
+        if (kConv1) { if (++sa == p.a_stages) { sa = 0; pa ^= 1; } }
         if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -565,10 +575,32 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
     // =========================== raw activation loader (TMA) ===========================
     if (!kConv1 && lane == 0) {
       int rs = 0; uint32_t pr = 0;
+      // The raw ring holds only 2-6 slabs (39-100 KB) per SM, too few bytes in flight to cover the DRAM
+      // latency of a whole tile; the rows of the tiles this CTA will work on next are therefore pulled
+      // into L2 ahead of time.  A tile's rows x all channels are ONE contiguous range of the activation.
+      const bool do_prefetch = p.prefetch_tiles > 0 && col0 == 0;    // one CTA of a column-split group is enough
+      auto prefetch_tile = [&](int tile) {
+        if (tile >= p.num_tiles) return;
+        const int m0 = tile * TILE_M, m1 = min(m0 + TILE_M, p.rows_out) - 1;
+        const int v0 = div_t_out(p, m0), t0 = m0 - v0 * p.t_out;
+        const int v1 = div_t_out(p, m1), t1 = m1 - v1 * p.t_out;
+        long long r0 = static_cast<long long>(v0) * p.t_in + t0 * kStride - p.pad_left;
+        long long r1 = static_cast<long long>(v1) * p.t_in + t1 * kStride - p.pad_left + 3;
+        r0 = r0 < 0 ? 0 : r0;
+        r1 = r1 > p.rows_in ? p.rows_in : r1;
+        const uint32_t row_bytes = static_cast<uint32_t>(p.cin) * 2u;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.in_act) + r0 * row_bytes;
+        const long long bytes = (r1 - r0) * row_bytes;
+        for (long long o = 0; o < bytes; o += 32768)
+          bulk_prefetch_l2(src + o, static_cast<uint32_t>(bytes - o < 32768 ? bytes - o : 32768));
+      };
+      if (do_prefetch)
+        for (int d = 1; d <= p.prefetch_tiles; ++d) prefetch_tile(tile0 + d * tstride);
       for (int tile = tile0; tile < p.num_tiles; tile += tstride) {
         const int m0 = tile * TILE_M;
         const int v0 = div_t_out(p, m0), t0 = m0 - v0 * p.t_out;
         const int lo = v0 * p.t_in + t0 * kStride - p.pad_left;
+        if (do_prefetch && tile != tile0) prefetch_tile(tile + p.prefetch_tiles * tstride);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&raw_empty[rs], pr ^ 1);
           mbar_arrive_expect_tx(&raw_full[rs], static_cast<uint32_t>(p.raw_stage_bytes));
@@ -892,10 +924,13 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
     if (lane == 0) bulk_wait_group_all();
   } else if (warp == FUSE_MMA_WARP) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // all 32 lanes walk the loop (uniform control flow and registers); one elected lane issues
+    {
       const uint32_t idesc1 = umma_idesc_f16(TILE_M, p.c0, /*fp16*/ 0);
       const uint32_t idesc2 = umma_idesc_f16(TILE_M, p.c1, /*fp16*/ 0);
-      const uint32_t a1 = smem_u32(a1_base), w1 = smem_u32(w1_base), w2 = smem_u32(w2_base), a2 = smem_u32(a2_base);
+      const uint32_t a1 = umma_desc_lo(smem_u32(a1_base)), w1 = umma_desc_lo(smem_u32(w1_base));
+      const uint32_t w2 = umma_desc_lo(smem_u32(w2_base)), a2 = umma_desc_lo(smem_u32(a2_base));
+      const uint32_t w1_slab = static_cast<uint32_t>(p.c0) * (ROW_BYTES >> 4), w2_slab = static_cast<uint32_t>(p.c1) * (ROW_BYTES >> 4);
       mbar_wait(w_full, 0);
       uint32_t ph_a1 = 0;
       auto issue_conv1 = [&](int i) {                            // conv1d_1 GEMM of this CTA's i-th unit
@@ -904,11 +939,16 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
         mbar_wait(a1_full, ph_a1); ph_a1 ^= 1u;
         tc_fence_after();
         const uint32_t d = tmem_base + static_cast<uint32_t>(s1 * p.c0);
-        for (int ks = 0; ks < 4; ++ks)
-          umma_f16(d, umma_desc_sw128(a1 + ks * 32), umma_desc_sw128(w1 + ks * 32), idesc1, ks != 0 ? 1u : 0u);
-        umma_f16(d, umma_desc_sw128(a1 + A_SLAB_BYTES), umma_desc_sw128(w1 + p.c0 * ROW_BYTES), idesc1, 1u);   // samples 64..79
-        umma_commit(a1_empty);
-        umma_commit(&acc1_full[s1]);
+        if (elect_one()) {
+          umma_f16_lo(d, a1, w1, idesc1, 0u);
+          umma_f16_lo(d, a1 + 2, w1 + 2, idesc1, 1u);
+          umma_f16_lo(d, a1 + 4, w1 + 4, idesc1, 1u);
+          umma_f16_lo(d, a1 + 6, w1 + 6, idesc1, 1u);
+          umma_f16_lo(d, a1 + (A_SLAB_BYTES >> 4), w1 + w1_slab, idesc1, 1u);   // samples 64..79
+          umma_commit(a1_empty);
+          umma_commit(&acc1_full[s1]);
+        }
+        __syncwarp();
       };
       int i = 0, n2 = 0;
       if (static_cast<int>(blockIdx.x) < p.num_units) issue_conv1(0);
@@ -922,13 +962,18 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
           mbar_wait(a2_full, static_cast<uint32_t>(n2) & 1u);
           tc_fence_after();
           const uint32_t d = tmem_base + acc2_col0 + static_cast<uint32_t>(s2 * p.c1);
-          const uint32_t a = a2;
-          for (int kb = 0; kb < nkb2; ++kb)
-            for (int ks = 0; ks < 4; ++ks)
-              umma_f16(d, umma_desc_sw128(a + kb * A_SLAB_BYTES + ks * 32),
-                       umma_desc_sw128(w2 + kb * p.c1 * ROW_BYTES + ks * 32), idesc2, (kb | ks) != 0 ? 1u : 0u);
-          umma_commit(a2_empty);
-          umma_commit(&acc2_full[s2]);
+          if (elect_one()) {
+            uint32_t a = a2, w = w2;
+            for (int kb = 0; kb < nkb2; ++kb, a += A_SLAB_BYTES >> 4, w += w2_slab) {
+              umma_f16_lo(d, a, w, idesc2, kb != 0 ? 1u : 0u);
+              umma_f16_lo(d, a + 2, w + 2, idesc2, 1u);
+              umma_f16_lo(d, a + 4, w + 4, idesc2, 1u);
+              umma_f16_lo(d, a + 6, w + 6, idesc2, 1u);
+            }
+            umma_commit(a2_empty);
+            umma_commit(&acc2_full[s2]);
+          }
+          __syncwarp();
         }
       }
     }
@@ -1106,7 +1151,8 @@ int launch_tc_gemm(kws_handle* h, GemmParams& p, cudaStream_t st) {
     // stride-2 ones have double-size raw stages, lose their TMA prefetch depth to the resident weights and get
     // slower, and 3/4-way splits re-read the raw rows more than they save in weight traffic.
     static const int max_split = [] { const char* e = getenv("KWS_MAX_SPLIT"); return e ? atoi(e) : 2; }();   // A/B aid
-    if (p.cout <= 256 || max_split < 2 || MODE != 1) {
+    static const bool split_s2 = [] { const char* e = getenv("KWS_SPLIT_S2"); return e && e[0] == '1'; }();           // A/B aid
+    if (p.cout <= 256 || max_split < 2 || (MODE != 1 && !split_s2)) {
       search(1, 1, false, 2);                                    // weights resident when they fit, else streamed
     } else {
       search(2, max_split, true, 1);
@@ -1297,6 +1343,9 @@ int launch_forward_tc(kws_handle* h, Model& m, const float* wav, int B, const Vi
       rc = make_tensor_map(h, &p.tmap_out, nxt, d.cout, static_cast<long long>(rows) * d.t_out, 1, 32, true);
       if (rc) return rc;
       p.block_index = i; p.out_act = nxt; p.out_rows = static_cast<long long>(rows) * d.t_out;
+      p.in_act = cur; p.rows_in = static_cast<long long>(rows) * d.t_in;
+      static const int prefetch_tiles = [] { const char* e = getenv("KWS_PREFETCH_TILES"); return e ? atoi(e) : 0; }();   // A/B aid
+      p.prefetch_tiles = prefetch_tiles;
       rc = d.stride == 1 ? launch_tc_gemm<1>(h, p, st) : launch_tc_gemm<2>(h, p, st);
       if (rc) return rc;
       std::swap(cur, nxt);
