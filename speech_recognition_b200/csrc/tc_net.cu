@@ -43,19 +43,18 @@ namespace {
 // group over a K = 80 GEMM), so it gets 8 epilogue warps (two per TMEM lane quarter, alternating
 // 64-column chunks), 6 producer warps and no raw-loader warp.
 template <int MODE> struct Roles {
-  static constexpr int EPI_WARPS = MODE == 0 ? 8 : 4;
+  static constexpr int EPI_WARPS = 8;
   static constexpr int MMA_WARP = EPI_WARPS;
   static constexpr int LOAD_WARP = EPI_WARPS + 1;
   static constexpr int RAW_WARP = MODE == 0 ? -1 : EPI_WARPS + 2;
   static constexpr int PROD_WARP0 = MODE == 0 ? EPI_WARPS + 2 : EPI_WARPS + 3;
   static constexpr int PROD_WARPS = MODE == 0 ? 6 : 8;
   static constexpr int PROD_THREADS = PROD_WARPS * 32;           // 192 / 256
-  static constexpr int THREADS = 32 * (PROD_WARP0 + PROD_WARPS); // 512 / 480
+  static constexpr int THREADS = 32 * (PROD_WARP0 + PROD_WARPS); // 512 / 608
 };
 constexpr int NUM_PROD_THREADS = Roles<1>::PROD_THREADS;         // dw_pw: 256
 constexpr int CONV1_PROD_THREADS = Roles<0>::PROD_THREADS;       // conv1: 192
-constexpr int PROD_GROUPS = 2;                                   // dw_pw: groups on alternate slabs
-constexpr int GROUP_THREADS = NUM_PROD_THREADS / PROD_GROUPS;    // 128
+constexpr int RUN_ROWS = TILE_M * 8 / NUM_PROD_THREADS;           // dw_pw: consecutive output rows per producer thread (4)
 constexpr int MAX_STAGES = 8;                                    // A / raw rings
 constexpr int MAX_B_BLOCKS = 16;                                 // B ring (K slabs x N halves)
 constexpr int TMEM_COLS = 512;
@@ -92,6 +91,8 @@ struct alignas(64) GemmParams {
   const __half* in_act;     // the previous activation itself (L2 prefetch of the rows of tiles ahead)
   long long rows_in;
   int prefetch_tiles;       // how many of this CTA's tiles ahead the raw loader prefetches into L2 (0 = off)
+  int knockout;             // KWS_KNOCKOUT (profiling only, results become wrong): 1 no TMA stores, 2 no FIR,
+                            // 4 no MMAs, 8 no epilogue math, 16 no raw loads
   // B side: pre-swizzled fp16 blocks of n_inst rows x 128 B, block j = (kb, nh) = (j / n_halves, j % n_halves)
   const uint8_t* w_img;
   // epilogue
@@ -131,11 +132,11 @@ __host__ __device__ inline SmemLayout smem_layout(const GemmParams& p, bool conv
   s.out_off = o; o += static_cast<uint32_t>((conv1 ? Roles<0>::EPI_WARPS : Roles<1>::EPI_WARPS) * p.out_bufs * OUT_STAGE_BYTES);
   s.raw_off = o; o += static_cast<uint32_t>(p.raw_stages) * p.raw_stage_bytes;
   s.aux_off = o;
-  // aux: shift[cout] fp32, then (dw_pw) taps [3*cin] fp16 + row metadata [2 groups][2 parities][128] u32
+  // aux: shift[cout] fp32, then (dw_pw) taps [3*cin] fp16 + row metadata [2 parities][128] u32
   //      or (conv1) the staged fp16 waveform window
   o += static_cast<uint32_t>(p.ncta) * 4u;
   o += conv1 ? 2u * CONV1_WIN_BYTES
-             : (static_cast<uint32_t>(3 * p.cin * 2 + 15) & ~15u) + PROD_GROUPS * 2 * TILE_M * 4u;
+             : (static_cast<uint32_t>(3 * p.cin * 2 + 15) & ~15u) + 2 * TILE_M * 4u;
   o = (o + 15u) & ~15u;
   s.bar_off = o; o += (4 * MAX_STAGES + 2 * MAX_B_BLOCKS + 4) * 8 + 16;
   s.total = o + 1024;        // slack for the manual 1024-byte alignment of the base
@@ -188,56 +189,59 @@ __device__ __forceinline__ uint4 fir3(const uint4& x0, const uint4& x1, const ui
   return o;
 }
 
-// One K slab (64 channels) of a 128-row tile by one producer group: thread = (16-byte channel
-// chunk c, run of 8 consecutive output rows).  raw = [box rows][64 ch] fp16 (dense 128-byte rows).
-// Fast path (the 8 rows continue one clip-view, i.e. almost always when T >= 47): every raw row of
-// the run is loaded up front (10 / 2x9 independent LDS.128), then the FIRs run from registers.
-template <int STRIDE>
-__device__ __forceinline__ void produce_slab(const uint8_t* raw, uint8_t* slab, const uint32_t* meta,
-                                             const __half* s_dwh, int cin, int kb, int tg) {
+// One K slab (64 channels) of a 128-row tile by the 256 producer threads: thread = (16-byte channel
+// chunk c, run of 4 consecutive output rows).  raw = [box rows][64 ch] fp16 (dense 128-byte rows).
+// The run is decoded once per tile (RunDesc); per slab the thread computes its 4 output chunks in
+// registers (fir_run) and only then waits for the A slot and stores them (store_run), so the raw
+// loads and the FIRs of slab k overlap the MMA that still reads the slot.
+// Fast path (the 4 rows continue one clip-view): every raw row of the run is loaded up front
+// (6 / 9 independent LDS.128), then the FIRs run from registers.  A run that crosses into the next
+// clip-view reloads its window at the crossing.
+struct RunDesc {
+  uint32_t mt[RUN_ROWS];    // row metadata words of the run
+  uint32_t base_off;        // byte offset of (first raw row, this thread's chunk) inside a raw stage
+  uint32_t dst_off[RUN_ROWS];   // swizzled byte offsets of the 4 output chunks inside an A slab
+  bool all_cont;
+};
+__device__ __forceinline__ RunDesc decode_run(const uint32_t* meta, int tg) {
+  RunDesc d;
   const int c = tg & 7, g = tg >> 3;
-  const int ch0 = kb * SLAB_K + c * 8;
-  const uint4 k0 = *reinterpret_cast<const uint4*>(s_dwh + ch0);
-  const uint4 k1 = *reinterpret_cast<const uint4*>(s_dwh + cin + ch0);
-  const uint4 k2 = *reinterpret_cast<const uint4*>(s_dwh + 2 * cin + ch0);
+  const uint4 m4 = *reinterpret_cast<const uint4*>(meta + RUN_ROWS * g);
+  d.mt[0] = m4.x; d.mt[1] = m4.y; d.mt[2] = m4.z; d.mt[3] = m4.w;
+  d.all_cont = (m4.y & m4.z & m4.w & (1u << 19)) != 0;
+  d.base_off = (m4.x & 0xffffu) * ROW_BYTES + c * 16;
+#pragma unroll
+  for (int i = 0; i < RUN_ROWS; ++i) d.dst_off[i] = swz_off(RUN_ROWS * g + i, c);
+  return d;
+}
+template <int STRIDE>
+__device__ __forceinline__ void fir_run(const uint8_t* raw, const RunDesc& d, const uint4& k0, const uint4& k1,
+                                        const uint4& k2, int c, uint4 (&o)[RUN_ROWS]) {
   const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-  const uint4 ma = *reinterpret_cast<const uint4*>(meta + 8 * g);
-  const uint4 mb = *reinterpret_cast<const uint4*>(meta + 8 * g + 4);
-  const uint32_t mt[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
-  const uint32_t all_cont = mt[1] & mt[2] & mt[3] & mt[4] & mt[5] & mt[6] & mt[7] & (1u << 19);
-  const uint8_t* base = raw + (mt[0] & 0xffffu) * ROW_BYTES + c * 16;
-  uint8_t* dst = slab + (8 * g) * ROW_BYTES;                     // rows 8g..8g+7 = one swizzle group
-  if (all_cont) {
+  if (d.all_cont) {
+    const uint8_t* base = raw + d.base_off;
     if (STRIDE == 1) {
-      uint4 x[10];
+      uint4 x[RUN_ROWS + 2];
 #pragma unroll
-      for (int i = 0; i < 10; ++i) x[i] = lds128(base + i * ROW_BYTES);
+      for (int i = 0; i < RUN_ROWS + 2; ++i) x[i] = lds128(base + i * ROW_BYTES);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        *reinterpret_cast<uint4*>(dst + i * ROW_BYTES + ((c ^ i) << 4)) = fir3(x[i], x[i + 1], x[i + 2], k0, k1, k2);
+      for (int i = 0; i < RUN_ROWS; ++i) o[i] = fir3(x[i], x[i + 1], x[i + 2], k0, k1, k2);
     } else {
+      uint4 x[2 * RUN_ROWS + 1];
 #pragma unroll
-      for (int hlf = 0; hlf < 2; ++hlf) {
-        uint4 x[9];
+      for (int i = 0; i < 2 * RUN_ROWS + 1; ++i) x[i] = lds128(base + i * ROW_BYTES);
+      if (!((d.mt[0] >> 16) & 1u)) x[0] = zero;                  // left 'SAME' pad: only a run's first row can be t = 0
+      if (!((d.mt[RUN_ROWS - 1] >> 18) & 1u)) x[2 * RUN_ROWS] = zero;   // right pad: only its last row can be t = T_out - 1
 #pragma unroll
-        for (int i = 0; i < 9; ++i) x[i] = lds128(base + (8 * hlf + i) * ROW_BYTES);
-        if (hlf == 0 && !((mt[0] >> 16) & 1u)) x[0] = zero;       // left 'SAME' pad: only a run's first row can be t = 0
-        if (hlf == 1 && !((mt[7] >> 18) & 1u)) x[8] = zero;       // right pad: only its last row can be t = T_out - 1
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = 4 * hlf + i;
-          *reinterpret_cast<uint4*>(dst + r * ROW_BYTES + ((c ^ r) << 4)) =
-              fir3(x[2 * i], x[2 * i + 1], x[2 * i + 2], k0, k1, k2);
-        }
-      }
+      for (int i = 0; i < RUN_ROWS; ++i) o[i] = fir3(x[2 * i], x[2 * i + 1], x[2 * i + 2], k0, k1, k2);
     }
     return;
   }
   uint4 w0 = zero, w1 = zero, w2 = zero;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const uint8_t* src = raw + (mt[i] & 0xffffu) * ROW_BYTES + c * 16;
-    const bool cont = (i > 0) && ((mt[i] >> 19) & 1u);
+  for (int i = 0; i < RUN_ROWS; ++i) {
+    const uint8_t* src = raw + (d.mt[i] & 0xffffu) * ROW_BYTES + c * 16;
+    const bool cont = (i > 0) && ((d.mt[i] >> 19) & 1u);
     if (STRIDE == 1) {
       // VALID convolution: every tap of a valid row is inside its clip
       if (cont) { w0 = w1; w1 = w2; }
@@ -245,11 +249,11 @@ __device__ __forceinline__ void produce_slab(const uint8_t* raw, uint8_t* slab, 
       w2 = lds128(src + 2 * ROW_BYTES);
     } else {
       if (cont) w0 = w2;
-      else w0 = ((mt[i] >> 16) & 1u) ? lds128(src) : zero;
+      else w0 = ((d.mt[i] >> 16) & 1u) ? lds128(src) : zero;
       w1 = lds128(src + ROW_BYTES);
-      w2 = ((mt[i] >> 18) & 1u) ? lds128(src + 2 * ROW_BYTES) : zero;
+      w2 = ((d.mt[i] >> 18) & 1u) ? lds128(src + 2 * ROW_BYTES) : zero;
     }
-    *reinterpret_cast<uint4*>(dst + i * ROW_BYTES + ((c ^ i) << 4)) = fir3(w0, w1, w2, k0, k1, k2);
+    o[i] = fir3(w0, w1, w2, k0, k1, k2);
   }
 }
 
@@ -401,13 +405,13 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
   if (warp == MMA_WARP) {
     if (lane == 0) {
       for (int i = 0; i < MAX_STAGES; ++i) {
-        mbar_init(&a_full[i], kConv1 ? CONV1_PROD_THREADS : GROUP_THREADS);
+        mbar_init(&a_full[i], (kConv1 ? CONV1_PROD_THREADS : NUM_PROD_THREADS) / 32);   // one arrival per warp
         mbar_init(&a_empty[i], 1);
         mbar_init(&raw_full[i], 1);
-        mbar_init(&raw_empty[i], GROUP_THREADS);
+        mbar_init(&raw_empty[i], NUM_PROD_THREADS / 32);
       }
       for (int i = 0; i < MAX_B_BLOCKS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NUM_EPI_WARPS * 32); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], NUM_EPI_WARPS); }
       fence_mbar_init();
     }
     __syncwarp();
@@ -450,6 +454,7 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
         row0 = tile * TILE_M + quarter * 32;
       }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * p.ncta);
+      if (p.knockout & 8) m1 = m0;
       for (int mem = m0; mem < m1; ++mem) {
         const float gain = kConv1 ? p.vg.gain[mem] : 1.0f;
         const int rv = kConv1 ? rv0 + p.vg.view[mem] : 0;
@@ -475,7 +480,7 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && !(p.knockout & 1)) {
             if (kConv1) tma_store_3d(&p.tmap_out, c0, row0, rv, box);
             else if (tail) tma_store_2d(&p.tmap_tail, col0 + c0, row0, box);
             else tma_store_2d(&p.tmap_out, col0 + c0, row0, box);
@@ -485,7 +490,8 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
         }
       }
       tc_fence_before();
-      mbar_arrive(&acc_empty[acc]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);             // 32 arrivals on one mbarrier word serialise: one per warp
       if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) bulk_wait_group_all();
@@ -521,8 +527,9 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
             tc_fence_after();
             if (elect_one()) {
               const uint32_t d = d0 + static_cast<uint32_t>(nh * p.n_inst);
-              umma_f16_lo(d, a_lo, b_lo, idesc, kb != 0 ? 1u : 0u);
-              if (ksteps == 4) {
+              if (!(p.knockout & 4)) umma_f16_lo(d, a_lo, b_lo, idesc, kb != 0 ? 1u : 0u);
+              if (p.knockout & 4) {
+              } else if (ksteps == 4) {
                 umma_f16_lo(d, a_lo + 2, b_lo + 2, idesc, 1u);
                 umma_f16_lo(d, a_lo + 4, b_lo + 4, idesc, 1u);
                 umma_f16_lo(d, a_lo + 6, b_lo + 6, idesc, 1u);
@@ -603,6 +610,7 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
         if (do_prefetch && tile != tile0) prefetch_tile(tile + p.prefetch_tiles * tstride);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&raw_empty[rs], pr ^ 1);
+          if (p.knockout & 16) { mbar_arrive(&raw_full[rs]); if (++rs == p.raw_stages) { rs = 0; pr ^= 1; } continue; }
           mbar_arrive_expect_tx(&raw_full[rs], static_cast<uint32_t>(p.raw_stage_bytes));
           uint8_t* dst = raw_base + rs * p.raw_stage_bytes;
           for (int bx = 0; bx < p.n_boxes; ++bx)
@@ -635,7 +643,8 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
         mbar_wait(&a_empty[sa], pa ^ 1);
         Conv1Producer::fill_slabs(a_base + sa * p.a_stage_bytes, ptid, win, cur.rows);
         fence_proxy_async_smem();
-        mbar_arrive(&a_full[sa]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[sa]);
         if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
         // no second barrier: the next tile writes the other window buffer, and this buffer is only
         // rewritten after the next tile's bar.sync, which every thread reaches after this fill
@@ -643,27 +652,38 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
         cur = nxt;
       }
     } else {
-      const int grp = ptid / GROUP_THREADS, tg = ptid - grp * GROUP_THREADS;
-      uint32_t* meta_g = s_meta + grp * 2 * TILE_M;
-      int n_base = 0, par = 0;                                   // n = running slab number of this CTA
+      // all 256 producer threads work on every slab, in ring order (any ring depth >= 2 works)
+      const int raw_stages = p.raw_stages, a_stages = p.a_stages, num_kb = p.num_kb;
+      const int c = ptid & 7;
+      int rs = 0, sa = 0, par = 0; uint32_t pr = 0, pa = 0;
       for (int tile = tile0; tile < p.num_tiles; tile += tstride) {
-        uint32_t* meta = meta_g + par * TILE_M;
-        meta[tg] = row_meta(p, kStride, tile, tg);
-        if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(GROUP_THREADS) : "memory");
-        else asm volatile("bar.sync 2, %0;" ::"n"(GROUP_THREADS) : "memory");
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          const int n = n_base + kb;
-          if ((n & 1) != grp) continue;
-          const int rs = n % p.raw_stages, sa = n % p.a_stages;
-          mbar_wait(&raw_full[rs], static_cast<uint32_t>(n / p.raw_stages) & 1u);
-          mbar_wait(&a_empty[sa], (static_cast<uint32_t>(n / p.a_stages) & 1u) ^ 1u);
-          produce_slab<kStride>(raw_base + rs * p.raw_stage_bytes, a_base + sa * p.a_stage_bytes, meta, s_dwh,
-                                p.cin, kb, tg);
+        uint32_t* meta = s_meta + par * TILE_M;
+        if (ptid < TILE_M) meta[ptid] = row_meta(p, kStride, tile, ptid);
+        asm volatile("bar.sync 1, %0;" ::"n"(NUM_PROD_THREADS) : "memory");
+        const RunDesc rd = decode_run(meta, ptid);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const __half* tp = s_dwh + kb * SLAB_K + c * 8;          // taps of this thread's 8 channels
+          const uint4 k0 = *reinterpret_cast<const uint4*>(tp);
+          const uint4 k1 = *reinterpret_cast<const uint4*>(tp + p.cin);
+          const uint4 k2 = *reinterpret_cast<const uint4*>(tp + 2 * p.cin);
+          uint4 o[RUN_ROWS];
+          mbar_wait(&raw_full[rs], pr);
+          if (p.knockout & 2) { o[0] = o[1] = o[2] = o[3] = k0; }
+          else fir_run<kStride>(raw_base + rs * p.raw_stage_bytes, rd, k0, k1, k2, c, o);
+          // every raw row of this slab has been consumed (the FIR outputs exist): the slot may be refilled
+          asm volatile("" ::"r"(o[0].x), "r"(o[1].x), "r"(o[2].x), "r"(o[3].x) : "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&raw_empty[rs]);            // one arrival per warp (32 on one word serialise)
+          mbar_wait(&a_empty[sa], pa ^ 1u);
+          uint8_t* slab = a_base + sa * p.a_stage_bytes;
+#pragma unroll
+          for (int i = 0; i < RUN_ROWS; ++i) *reinterpret_cast<uint4*>(slab + rd.dst_off[i]) = o[i];
           fence_proxy_async_smem();
-          mbar_arrive(&a_full[sa]);
-          mbar_arrive(&raw_empty[rs]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[sa]);
+          if (++rs == raw_stages) { rs = 0; pr ^= 1u; }
+          if (++sa == a_stages) { sa = 0; pa ^= 1u; }
         }
-        n_base += p.num_kb;
         par ^= 1;
       }
     }
@@ -1101,47 +1121,50 @@ int launch_tc_gemm(kws_handle* h, GemmParams& p, cudaStream_t st) {
     p.b_resident = 1;
     chosen = fits(3, blocks, 0) || fits(2, blocks, 0);
   } else {
-    // The two producer groups work on alternate slabs, so the A and raw rings need EVEN depths: with
-    // slot = n % depth every slot then belongs to one group, and no thread ever waits on an mbarrier
-    // more than one phase ahead of it (a group that skipped a slot's previous use would otherwise
-    // see a stale parity).
     // Wide layers (cout > 256) cannot double-buffer their accumulator in TMEM nor keep their weights
     // in shared memory, which serialises MMA and epilogue and re-streams up to 512 KB of weights per
     // tile from L2.  They are split column-wise over 2-4 adjacent CTAs instead: each CTA keeps its
     // slice of the weights resident for the whole launch and owns two accumulator stages; the A
     // operand of a row tile is then produced once per slice (its raw rows come from L2 after the
-    // first CTA touched them).  Preference: smallest split with resident weights, deep A ring, deep raw ring.
-    const int r_min = MODE == 1 ? 4 : 2;
+    // first CTA touched them).  Preference: smallest split with resident weights, deep raw ring, deep A ring.
+    // (The producers fill the rings strictly in order, so any depth >= 2 is valid.)
+    static const int force_a = [] { const char* e = getenv("KWS_A_STAGES"); return e ? atoi(e) : 0; }();       // A/B aids
+    static const int force_r = [] { const char* e = getenv("KWS_RAW_STAGES"); return e ? atoi(e) : 0; }();
+    auto fits_f = [&](int a, int b, int r) {
+      if ((force_a && a != force_a) || (force_r && r != force_r)) return false;
+      return fits(a, b, r);
+    };
+    const int r_min = MODE == 1 ? 3 : 2;
     auto search = [&](int ns_lo, int ns_hi, bool resident_only, int ob_lo) {
       for (int ns = ns_lo; ns <= ns_hi && !chosen; ++ns) {
         if (!set_split(ns)) continue;
         const int blocks = p.num_kb * p.n_halves;
         const int b_block = p.n_inst * ROW_BYTES;
         const int b_stream = std::max(2, std::min(4, 65536 / b_block));
-        if (ob_lo == 2) {                                        // narrow layers: deep A ring first
+        if (ob_lo == 2) {                                        // narrow layers
           // resident weights first (measured: 192->192 with resident weights and a 2-deep A ring beats streamed
           // weights with a 4-deep A ring by 8 %), then streamed weights with the deepest rings that fit
-          p.out_bufs = 2;
+          p.out_bufs = 1;                                        // two epilogue warps per lane quarter alternate: one box each
           if (blocks <= MAX_B_BLOCKS)
-            for (int r = 6; r >= r_min && !chosen; r -= 2)          // TMA prefetch depth matters more than A-ring depth
-              for (int a = 4; a >= 2 && !chosen; a -= 2)
-                if (fits(a, blocks, r)) { p.b_resident = 1; chosen = true; }
-          for (int a = 4; a >= 2 && !chosen; a -= 2)
+            for (int r = 6; r >= r_min && !chosen; --r)            // TMA prefetch depth matters more than A-ring depth
+              for (int a = 4; a >= 2 && !chosen; --a)
+                if (fits_f(a, blocks, r)) { p.b_resident = 1; chosen = true; }
+          for (int a = 4; a >= 2 && !chosen; --a)
             for (int res = 1; res >= (resident_only ? 1 : 0) && !chosen; --res) {
               if (res && blocks > MAX_B_BLOCKS) continue;
               for (int bs = res ? blocks : b_stream; bs >= (res ? blocks : 2) && !chosen; --bs)
-                for (int r = 6; r >= r_min && !chosen; r -= 2)
-                  if (fits(a, bs, r)) { p.b_resident = res; chosen = true; }
+                for (int r = 6; r >= 2 && !chosen; --r)
+                  if (fits_f(a, bs, r)) { p.b_resident = res; chosen = true; }
             }
         } else {                                                 // split layers: deep raw ring (HBM/L2 latency) first
           for (int res = 1; res >= (resident_only ? 1 : 0) && !chosen; --res) {
             if (res && blocks > MAX_B_BLOCKS) continue;
-            for (int r = 6; r >= 2 && !chosen; r -= 2)
-              for (int ob = 2; ob >= 1 && !chosen; --ob) {
+            for (int r = 6; r >= 2 && !chosen; --r)
+              for (int ob = 1; ob >= 1 && !chosen; --ob) {
                 p.out_bufs = ob;
-                for (int a = 4; a >= 2 && !chosen; a -= 2)
+                for (int a = 4; a >= 2 && !chosen; --a)
                   for (int bs = res ? blocks : b_stream; bs >= (res ? blocks : 2) && !chosen; --bs)
-                    if (fits(a, bs, r)) { p.b_resident = res; chosen = true; }
+                    if (fits_f(a, bs, r)) { p.b_resident = res; chosen = true; }
               }
           }
         }
@@ -1171,6 +1194,8 @@ int launch_tc_gemm(kws_handle* h, GemmParams& p, cudaStream_t st) {
     const int rc = make_tensor_map(h, &p.tmap_tail, p.out_act, p.cout, p.out_rows, 1, 32, false, 32);
     if (rc) return rc;
   }
+  static const int knockout = [] { const char* e = getenv("KWS_KNOCKOUT"); return e ? atoi(e) : 0; }();
+  p.knockout = knockout;
   KWS_T0(h, MODE == 0 ? KC_CONV1 : KC_BLOCK0 + p.block_index, st);
   tc_gemm_kernel<MODE><<<grid, Roles<MODE>::THREADS, lay.total, st>>>(p);
   KWS_T1(h, st);

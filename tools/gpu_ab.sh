@@ -2,7 +2,7 @@
 # A/B of an environment switch on the bench's per-block times.  Usage: gpurun -- bash tools/gpu_ab.sh "VAR=a" "VAR=b" ...
 mkdir -p gpurun_out
 for CFG in "$@"; do
-  env $CFG timeout -s KILL 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ab.json 2>gpurun_out/ab.err
+  env $CFG timeout -s KILL 200 python bench.py --steps ${AB_STEPS:-5} --warmup 3 --no-cpu-baseline ${AB_ARGS} > gpurun_out/ab.json 2>gpurun_out/ab.err
   python - "$CFG" <<'PY'
 import json,sys
 try:
