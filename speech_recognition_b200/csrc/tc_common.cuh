@@ -57,6 +57,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity) {   // bar_addr = shared-space address
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar_addr), "r"(parity)
+      : "memory");
+}
+
 // generic-proxy writes (st.shared) -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -210,6 +223,12 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Pinning kernel parameters in registers: parameters live in the constant bank, and ptxas prefers
+// re-loading them (LDC / LDCU, tens of cycles each, serialised by the surrounding mbarrier waits) to
+// keeping them live across a loop; in the single-warp pipeline roles those reloads were a large part
+// of the per-slab latency.  The kernels add a zero that is read from shared memory at run time
+// (`+ z`): the sum cannot be rematerialised from the constant bank, so it stays in a register.
+
 // The MMA warps run their loops with all 32 lanes converged and elect one lane only around the
 // tcgen05 instructions: addresses, stage counters and descriptors then live in uniform registers
 // (a loop under `if (lane == 0)` is divergent code, and the compiler re-broadcasts every descriptor
@@ -244,6 +263,54 @@ __device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t a_lo, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
       "}" ::"r"(tmem_d),
       "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_HI)
+      : "memory");
+}
+// One K slab (4 x K=16) of MMAs plus up to two commits as ONE predicated instruction sequence: every
+// lane computes the descriptors (uniform), the elected lane issues.  No divergent region, no per-MMA
+// descriptor re-broadcast; bar1 / bar2 = shared-memory addresses of mbarriers to commit to (0 = none).
+__device__ __forceinline__ void umma_slab4_commit(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                                  uint32_t accumulate_first, uint32_t bar1, uint32_t bar2) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe, pa, pt, p1, p2;\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .b32 ax, bx;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "setp.ne.and.b32 p1, %5, 0, pe;\n\t"
+      "setp.ne.and.b32 p2, %6, 0, pe;\n\t"
+      "mov.b64 da, {%1, %7};\n\t"
+      "mov.b64 db, {%2, %7};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pa;\n\t"
+      "add.u32 ax, %1, 2;\n\t"
+      "add.u32 bx, %2, 2;\n\t"
+      "mov.b64 da, {ax, %7};\n\t"
+      "mov.b64 db, {bx, %7};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "add.u32 ax, %1, 4;\n\t"
+      "add.u32 bx, %2, 4;\n\t"
+      "mov.b64 da, {ax, %7};\n\t"
+      "mov.b64 db, {bx, %7};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "add.u32 ax, %1, 6;\n\t"
+      "add.u32 bx, %2, 6;\n\t"
+      "mov.b64 da, {ax, %7};\n\t"
+      "mov.b64 db, {bx, %7};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "@p1 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t"
+      "@p2 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate_first), "r"(bar1), "r"(bar2), "r"(UMMA_DESC_HI)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {      // all lanes call; the elected lane commits
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(bar)
       : "memory");
 }
 // mbarrier arrives once every tcgen05 op issued so far by this thread has completed
