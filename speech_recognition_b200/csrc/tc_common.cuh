@@ -43,17 +43,21 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or the time hint expires.  Without a
+// hint the default limit is a few cycles, and a waiting role re-issues try_wait + branch every ~20 cycles:
+// a dozen waiting warps then burn issue slots and LSU bandwidth that the working warps need.
+constexpr uint32_t MBAR_SUSPEND_NS = 100000u;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra WAIT_DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t"
-      "}" ::"r"(a), "r"(parity)
+      "}" ::"r"(a), "r"(parity), "r"(MBAR_SUSPEND_NS)
       : "memory");
 }
 
@@ -62,12 +66,32 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parit
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra WAIT_DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t"
-      "}" ::"r"(bar_addr), "r"(parity)
+      "}" ::"r"(bar_addr), "r"(parity), "r"(MBAR_SUSPEND_NS)
       : "memory");
+}
+
+// Non-blocking probes of two mbarriers at once: the two round trips to the barrier unit (~150 cycles each,
+// even when the phase completed long ago) overlap; bit 0 / bit 1 of the result = phase 1 / 2 complete.
+__device__ __forceinline__ uint32_t mbar_test2(uint64_t* bar1, uint32_t parity1, uint64_t* bar2, uint32_t parity2) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p1, p2;\n\t"
+      ".reg .b32 r1, r2;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p1, [%1], %2;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p2, [%3], %4;\n\t"
+      "selp.u32 r1, 1, 0, p1;\n\t"
+      "selp.u32 r2, 2, 0, p2;\n\t"
+      "or.b32 %0, r1, r2;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar1)), "r"(parity1), "r"(smem_u32(bar2)), "r"(parity2)
+      : "memory");
+  return ok;
 }
 
 // generic-proxy writes (st.shared) -> visible to the async proxy (tcgen05.mma operand reads)
@@ -302,6 +326,46 @@ __device__ __forceinline__ void umma_slab4_commit(uint32_t tmem_d, uint32_t a_lo
       "@p2 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
       "}" ::"r"(tmem_d),
       "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate_first), "r"(bar1), "r"(bar2), "r"(UMMA_DESC_HI)
+      : "memory");
+}
+// same with a run-time number of K steps (1..4): the last K slab of a contraction whose K is not a multiple of 64
+__device__ __forceinline__ void umma_slab_commit(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                                 uint32_t accumulate_first, uint32_t ksteps, uint32_t bar1, uint32_t bar2) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe, pa, pt, p1, p2, q1, q2, q3;\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .b32 ax, bx;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "setp.ne.and.b32 p1, %5, 0, pe;\n\t"
+      "setp.ne.and.b32 p2, %6, 0, pe;\n\t"
+      "setp.gt.and.u32 q1, %8, 1, pe;\n\t"
+      "setp.gt.and.u32 q2, %8, 2, pe;\n\t"
+      "setp.gt.and.u32 q3, %8, 3, pe;\n\t"
+      "mov.b64 da, {%1, %7};\n\t"
+      "mov.b64 db, {%2, %7};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pa;\n\t"
+      "add.u32 ax, %1, 2;\n\t"
+      "add.u32 bx, %2, 2;\n\t"
+      "mov.b64 da, {ax, %7};\n\t"
+      "mov.b64 db, {bx, %7};\n\t"
+      "@q1 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "add.u32 ax, %1, 4;\n\t"
+      "add.u32 bx, %2, 4;\n\t"
+      "mov.b64 da, {ax, %7};\n\t"
+      "mov.b64 db, {bx, %7};\n\t"
+      "@q2 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "add.u32 ax, %1, 6;\n\t"
+      "add.u32 bx, %2, 6;\n\t"
+      "mov.b64 da, {ax, %7};\n\t"
+      "mov.b64 db, {bx, %7};\n\t"
+      "@q3 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "@p1 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t"
+      "@p2 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate_first), "r"(bar1), "r"(bar2), "r"(UMMA_DESC_HI), "r"(ksteps)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {      // all lanes call; the elected lane commits

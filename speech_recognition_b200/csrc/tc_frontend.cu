@@ -207,58 +207,39 @@ __global__ void __launch_bounds__(F_THREADS, 1) stft_mel_tc_kernel(const DftPara
     }
   } else if (warp == F_MMA_WARP) {
     // =========================== MMA issuer ===========================
-    // all 32 lanes walk the loop (uniform control flow and registers); one elected lane issues
+    // all 32 lanes walk the loop (uniform control flow and registers); one elected lane issues.  Each
+    // (A slab, basis block) pass is one predicated PTX sequence (tc_common.cuh umma_slab_commit).
     {
       const uint32_t idesc = umma_idesc_f16(TILE_M, F_NH, /*fp16*/ 0);
       const uint32_t a_lo0 = umma_desc_lo(smem_u32(a_base)), b_lo0 = umma_desc_lo(smem_u32(b_base));
-      const int num_kb = p.num_kb, last_ksteps = p.last_ksteps, b_stages = p.b_stages;
+      const uint32_t a_full0 = smem_u32(a_full), a_empty0 = smem_u32(a_empty), b_full0 = smem_u32(b_full), b_empty0 = smem_u32(b_empty);
+      const int num_kb = p.num_kb, last_ksteps = p.last_ksteps, b_stages = p.b_stages, num_tiles = p.num_tiles;
       int sa = 0; uint32_t pa = 0; int sb = 0; uint32_t pb = 0; uint32_t acc_phase = 0;
-      // one pass = ksteps MMAs of A slab `a` against the B block in slot sb
-      auto pass = [&](uint32_t d, uint32_t a, uint32_t b, int ksteps, uint32_t first_acc) {
-        umma_f16_lo(d, a, b, idesc, first_acc);
-        if (ksteps == 4) {
-          umma_f16_lo(d, a + 2, b + 2, idesc, 1u);
-          umma_f16_lo(d, a + 4, b + 4, idesc, 1u);
-          umma_f16_lo(d, a + 6, b + 6, idesc, 1u);
-        } else {
-          for (int ks = 1; ks < ksteps; ++ks) umma_f16_lo(d, a + 2 * ks, b + 2 * ks, idesc, 1u);
-        }
-      };
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(acc_empty, acc_phase ^ 1);
-        tc_fence_after();
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&a_full[sa], pa);
+          mbar_wait_addr(a_full0 + 8u * sa, pa);
           const uint32_t a_hi = a_lo0 + static_cast<uint32_t>(sa) * (F_A_STAGE >> 4);
           const uint32_t a_lo = a_hi + (A_SLAB_BYTES >> 4);
-          const int ksteps = (kb == num_kb - 1) ? last_ksteps : 4;
+          const uint32_t ksteps = (kb == num_kb - 1) ? static_cast<uint32_t>(last_ksteps) : 4u;
           for (int nh = 0; nh < 2; ++nh) {
             const uint32_t d = tmem_base + nh * F_NH;
-            mbar_wait(&b_full[sb], pb);
+            mbar_wait_addr(b_full0 + 8u * sb, pb);
             tc_fence_after();
-            if (elect_one()) {
-              const uint32_t b = b_lo0 + static_cast<uint32_t>(sb) * (F_B_BLOCK >> 4);
-              pass(d, a_hi, b, ksteps, kb != 0 ? 1u : 0u);
-              pass(d, a_lo, b, ksteps, 1u);
-              umma_commit(&b_empty[sb]);
-            }
-            __syncwarp();
+            uint32_t b = b_lo0 + static_cast<uint32_t>(sb) * (F_B_BLOCK >> 4);
+            umma_slab_commit(d, a_hi, b, idesc, kb != 0 ? 1u : 0u, ksteps, 0u, 0u);          // x_hi * b_hi
+            umma_slab_commit(d, a_lo, b, idesc, 1u, ksteps, b_empty0 + 8u * sb, 0u);            // x_lo * b_hi
             if (++sb == b_stages) { sb = 0; pb ^= 1; }
-            mbar_wait(&b_full[sb], pb);
+            mbar_wait_addr(b_full0 + 8u * sb, pb);
             tc_fence_after();
-            if (elect_one()) {
-              const uint32_t b = b_lo0 + static_cast<uint32_t>(sb) * (F_B_BLOCK >> 4);
-              pass(d, a_hi, b, ksteps, 1u);
-              umma_commit(&b_empty[sb]);
-              if (nh == 1) umma_commit(&a_empty[sa]);
-            }
-            __syncwarp();
+            b = b_lo0 + static_cast<uint32_t>(sb) * (F_B_BLOCK >> 4);
+            umma_slab_commit(d, a_hi, b, idesc, 1u, ksteps, b_empty0 + 8u * sb,                  // x_hi * b_lo
+                             nh == 1 ? a_empty0 + 8u * sa : 0u);
             if (++sb == b_stages) { sb = 0; pb ^= 1; }
           }
           if (++sa == F_A_STAGES) { sa = 0; pa ^= 1; }
         }
-        if (elect_one()) umma_commit(acc_full);
-        __syncwarp();
+        umma_commit_elect(smem_u32(acc_full));
         acc_phase ^= 1;
       }
     }

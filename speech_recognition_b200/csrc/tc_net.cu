@@ -8,15 +8,18 @@
 //                      make_submission.py:126-130) is applied while the waveform window is staged.
 //   * K6 dw_pw_block : depthwise k3 FIR (CUDA cores) as the A-operand producer of the pointwise
 //                      GEMM, BN + ReLU6 in the epilogue.
-// Roles (480 threads, 1 CTA / SM, static round-robin over 128-row tiles):
-//   warps 0-3  epilogue   : tcgen05.ld accumulator -> +shift -> ReLU6 -> fp16 -> global
-//   warp  4    MMA        : one thread issues tcgen05.mma (A,B from swizzled smem, D in TMEM)
-//   warp  5    B loader   : cp.async.bulk of pre-swizzled fp16 weight blocks (resident when they fit)
-//   warp  6    raw loader : cp.async.bulk.tensor (TMA) of the previous activation's rows, one
-//                           [rows x 64 channel] box per K slab, several slabs ahead of the producers
-//   warps 7-14 A producers: two groups of 128 threads working on alternate K slabs; each thread
-//                           slides a 3-row window over 8 consecutive output rows of one 8-channel
-//                           chunk (packed half2 FMAs) and stores the UMMA-swizzled A slab
+// Roles of a dw_pw block (608 threads, 1 CTA / SM, static round-robin over 128-row tiles):
+//   warps 0-7   epilogue   : tcgen05.ld accumulator -> +shift -> ReLU6 -> fp16 -> swizzled smem box -> TMA store
+//                            (two warps per TMEM lane quarter on alternate 64-column chunks)
+//   warp  8     MMA        : all lanes walk the loop, one elected lane issues; one predicated PTX sequence
+//                            per K slab (4 x tcgen05.mma + the commits), A,B from swizzled smem, D in TMEM
+//   warp  9     B loader   : cp.async.bulk of pre-swizzled fp16 weight blocks (resident when they fit)
+//   warp  10    raw loader : cp.async.bulk.tensor (TMA) of the previous activation's rows, one
+//                            [rows x 64 channel] box per K slab, several slabs ahead of the producers
+//   warps 11-18 A producers: 256 threads fill the A ring in order; each thread slides a 3-row window over
+//                            4 consecutive output rows of one 8-channel chunk (packed half2 FMAs: the FIR
+//                            outputs are complete before it waits for the A slot) and stores the
+//                            UMMA-swizzled A slab; one mbarrier arrival per warp
 // Pipelines: raw ring (TMA <-> producers), A ring (producers <-> MMA), B ring (loader <-> MMA),
 // accumulator stages in TMEM (MMA <-> epilogue), all on mbarriers; tcgen05.commit releases smem
 // slots / publishes accumulators.
@@ -24,8 +27,10 @@
 // [0,6] so the range is safe), accumulation is fp32 in TMEM.  The BatchNorm scale is folded into
 // the fp16 weights at load time, the shift stays fp32 in the epilogue.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include <cuda.h>
 
@@ -91,6 +96,7 @@ struct alignas(64) GemmParams {
   const __half* in_act;     // the previous activation itself (L2 prefetch of the rows of tiles ahead)
   long long rows_in;
   int prefetch_tiles;       // how many of this CTA's tiles ahead the raw loader prefetches into L2 (0 = off)
+  unsigned long long* trace;   // KWS_TRACE=<block index> (profiling only): per-role event log of CTA 0, see trace_ev
   int knockout;             // KWS_KNOCKOUT (profiling only, results become wrong): 1 no TMA stores, 2 no FIR,
                             // 4 no MMAs, 8 no epilogue math, 16 no raw loads
   // B side: pre-swizzled fp16 blocks of n_inst rows x 128 B, block j = (kb, nh) = (j / n_halves, j % n_halves)
@@ -360,6 +366,18 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const fl
   }
 }
 
+// Event log for pipeline analysis (KWS_TRACE=<block index>, tools/gpu_trace.sh, tools/trace_view.py): role r
+// owns records [r * TRACE_EVENTS, (r + 1) * TRACE_EVENTS), record = (event << 56 | index << 40 | clock64 & (2^40-1));
+// only CTA 0 writes, one thread per role.  p.trace == nullptr (always, unless KWS_TRACE is set) disables it.
+constexpr int TRACE_EVENTS = 4096, TRACE_ROLES = 4;
+__device__ __forceinline__ void trace_ev(unsigned long long* trace, int role, int& cnt, int ev, int idx) {
+  if (trace != nullptr && blockIdx.x == 0 && cnt < TRACE_EVENTS) {
+    const unsigned long long c = static_cast<unsigned long long>(clock64());
+    trace[role * TRACE_EVENTS + cnt++] = (static_cast<unsigned long long>(ev) << 56) |
+                                         (static_cast<unsigned long long>(idx & 0xffff) << 40) | (c & ((1ull << 40) - 1));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
@@ -426,6 +444,7 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t z = reinterpret_cast<volatile uint32_t*>(tmem_slot)[1];
   const int zi = static_cast<int>(z);
+  unsigned long long* const trace = p.trace + z;
   const uint32_t b_block_bytes = static_cast<uint32_t>(p.n_inst) * ROW_BYTES;
   const int blocks_per_tile = p.num_kb * p.n_halves;
 
@@ -442,8 +461,11 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
     const int quarter = warp & 3, c_first = (warp >> 2) * 64;
     constexpr int c_step = 64 * kColGroups;
     if (lane == 0) tma_prefetch_desc(&p.tmap_out);
+    int tcnt = 0, tidx = 0;
     for (int tile = tile0; tile < p.num_tiles; tile += tstride) {
+      if (warp == 0 && lane == 0) trace_ev(trace, 0, tcnt, 1, tidx);
       mbar_wait(&acc_full[acc], acc_phase);
+      if (warp == 0 && lane == 0) trace_ev(trace, 0, tcnt, 2, tidx);
       tc_fence_after();
       int row0, rv0 = 0, m0 = 0, m1 = 1;                         // first output row of this warp's box; member views
       if (kConv1) {
@@ -494,7 +516,8 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);             // 32 arrivals on one mbarrier word serialise: one per warp
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);             // one arrival per warp
+      if (warp == 0 && lane == 0) trace_ev(trace, 0, tcnt, 3, tidx++);
       if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) bulk_wait_group_all();
@@ -527,12 +550,16 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
         // slot (streamed weights) and, after the last N half, the A stage.
         const uint32_t a_full0 = smem_u32(a_full) + z, a_free0 = smem_u32(a_free) + z, b_full0 = smem_u32(b_full) + z;
         const uint32_t b_empty0 = smem_u32(b_empty) + z, acc_full0 = smem_u32(acc_full) + z;
+        int tcnt = 0, tn = 0;
         for (int tile = tile0; tile < num_tiles; tile += tstep) {
+          if (lane == 0) trace_ev(trace, 1, tcnt, 1, tn);
           mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+          if (lane == 0) trace_ev(trace, 1, tcnt, 2, tn);
           const uint32_t d0 = tmem0 + static_cast<uint32_t>(acc * ncta);
           uint32_t b_lo = b_lo0;                                 // resident: block j = (kb, nh) in order
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait_addr(a_full0 + 8u * sa, pa);
+            if (lane == 0) trace_ev(trace, 1, tcnt, 3, tn);
             const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(sa) * a_stage_lo;
             const uint32_t a_bar = a_free0 + 8u * sa;
             if (resident && n_halves == 1) {
@@ -555,6 +582,7 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
                 else b_lo += b_block_lo;
               }
             }
+            if (lane == 0) trace_ev(trace, 1, tcnt, 4, tn++);
             if (++sa == a_depth) { sa = 0; pa ^= 1; }
           }
           umma_commit_elect(acc_full0 + 8u * acc);
@@ -624,6 +652,7 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
     // =========================== raw activation loader (TMA) ===========================
     if (!kConv1 && lane == 0) {
       int rs = 0; uint32_t pr = 0;
+      int tcnt = 0, tn = 0;
       // The raw ring holds only 2-6 slabs (39-100 KB) per SM, too few bytes in flight to cover the DRAM
       // latency of a whole tile; the rows of the tiles this CTA will work on next are therefore pulled
       // into L2 ahead of time.  A tile's rows x all channels are ONE contiguous range of the activation.
@@ -651,7 +680,9 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
         const int lo = v0 * p.t_in + t0 * kStride - p.pad_left;
         if (do_prefetch && tile != tile0) prefetch_tile(tile + p.prefetch_tiles * tstride);
         for (int kb = 0; kb < p.num_kb; ++kb) {
+          trace_ev(trace, 2, tcnt, 1, tn);
           mbar_wait(&raw_empty[rs], pr ^ 1);
+          trace_ev(trace, 2, tcnt, 2, tn++);
           if (p.knockout & 16) { mbar_arrive(&raw_full[rs]); if (++rs == p.raw_stages) { rs = 0; pr ^= 1; } continue; }
           mbar_arrive_expect_tx(&raw_full[rs], static_cast<uint32_t>(p.raw_stage_bytes));
           uint8_t* dst = raw_base + rs * p.raw_stage_bytes;
@@ -701,6 +732,7 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
       const bool ko_fir = ((p.knockout & 2) + zi) != 0;
       const int c = ptid & 7;
       int rs = 0, sa = 0, par = 0; uint32_t pr = 0, pa = 0;
+      int tcnt = 0, tn = 0;
       for (int tile = tile0; tile < num_tiles; tile += tstep) {
         uint32_t* meta = s_meta + par * TILE_M;
         if (ptid < TILE_M) meta[ptid] = row_meta(p, kStride, tile, ptid);
@@ -712,20 +744,25 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
           const uint4 k1 = *reinterpret_cast<const uint4*>(tp + cin);
           const uint4 k2 = *reinterpret_cast<const uint4*>(tp + 2 * cin);
           uint4 o[RUN_ROWS];
+          if (ptid == 0) trace_ev(trace, 3, tcnt, 1, tn);
           mbar_wait(&raw_full[rs], pr);
+          if (ptid == 0) trace_ev(trace, 3, tcnt, 2, tn);
           if (ko_fir) { o[0] = o[1] = o[2] = o[3] = k0; }
           else fir_run<kStride>(raw_base + rs * raw_stage_bytes, rd, k0, k1, k2, c, o);
           // every raw row of this slab has been consumed (the FIR outputs exist): the slot may be refilled
           asm volatile("" ::"r"(o[0].x), "r"(o[1].x), "r"(o[2].x), "r"(o[3].x) : "memory");
           __syncwarp();
-          if (lane == 0) mbar_arrive(&raw_empty[rs]);            // one arrival per warp (32 on one word serialise)
+          if (lane == 0) mbar_arrive(&raw_empty[rs]);            // one arrival per warp
+          if (ptid == 0) trace_ev(trace, 3, tcnt, 3, tn);
           mbar_wait(&a_empty[sa], pa ^ 1u);
+          if (ptid == 0) trace_ev(trace, 3, tcnt, 4, tn);
           uint8_t* slab = a_base + sa * a_stage_bytes;
 #pragma unroll
           for (int i = 0; i < RUN_ROWS; ++i) *reinterpret_cast<uint4*>(slab + rd.dst_off[i]) = o[i];
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_full[sa]);
+          if (ptid == 0) trace_ev(trace, 3, tcnt, 5, tn++);
           if (++rs == raw_stages) { rs = 0; pr ^= 1u; }
           if (++sa == a_stages) { sa = 0; pa ^= 1u; }
         }
@@ -792,8 +829,10 @@ __host__ __device__ inline FusedSmem fused_smem(int c0, int c1) {
   s.a1 = o; o += 2 * A_SLAB_BYTES;
   s.w1 = o; o += 2u * c0 * ROW_BYTES;
   s.w2 = o; o += static_cast<uint32_t>(c0 / SLAB_K) * c1 * ROW_BYTES;
-  s.a2 = o; o += static_cast<uint32_t>(c0 / SLAB_K) * A_SLAB_BYTES;     // one stage: the next view's pack phase covers its MMA
-  s.raw = o; o += static_cast<uint32_t>(c0 / SLAB_K) * A_SLAB_BYTES;    // relu6(bn(conv1d_1)) rows of one view, swizzled like a slab
+  // two row buffers: relu6(bn(conv1d_1)) rows of one view, swizzled like A slabs, FIR-filtered IN PLACE into the A
+  // operand of the pointwise GEMM; view v + 1 is packed and filtered in the other buffer while the MMA reads this one
+  s.a2 = o; o += 2u * static_cast<uint32_t>(c0 / SLAB_K) * A_SLAB_BYTES;
+  s.raw = s.a2;
   s.out = o; o += FUSE_OUT_WARPS * OUT_STAGE_BYTES;                      // (the FIR of the last rows reads 2 rows past a raw slab: into the next region)
   s.win = o; o += 2 * CONV1_WIN_BYTES;
   s.sh1 = o; o += c0 * 4u;
@@ -842,8 +881,8 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
   uint64_t* a1_empty = bars + 1;       // [1]
   uint64_t* acc1_full = bars + 2;      // [2]
   uint64_t* acc1_empty = bars + 4;     // [2]
-  uint64_t* a2_full = bars + 6;        // [1] (+1 unused)
-  uint64_t* a2_empty = bars + 8;       // [1] (+1 unused)
+  uint64_t* a2_full = bars + 6;        // [2]
+  uint64_t* a2_empty = bars + 8;       // [2]
   uint64_t* acc2_full = bars + 10;     // [2]
   uint64_t* acc2_empty = bars + 12;    // [2]
   uint64_t* w_full = bars + 14;        // [1]
@@ -892,6 +931,7 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
     const int nchw = nch / 2, ch0 = hf * nchw;                   // pack phase: this warp's 16-byte channel chunks [ch0, ch0 + nchw)
     const int fkb = tid >> 7, ftg = tid & 127;                   // FIR phase: K slab and (chunk, 8-row run) of this thread
     const int fc = ftg & 7, fg = ftg >> 3;
+    const uint32_t buf_bytes = static_cast<uint32_t>(nkb2) * A_SLAB_BYTES;
     int n2 = 0, i = 0;
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++i) {
       int b, g, j; decode(unit, b, g, j);
@@ -904,6 +944,9 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
       const bool fir_on = fkb < nkb2 && 8 * fg < p.t2 - j * FUSE_ROWS;
       for (int mem = p.vg.start[g]; mem < p.vg.start[g + 1]; ++mem, ++n2) {
         const float gain = p.vg.gain[mem];
+        const int bsel = n2 & 1;
+        uint8_t* buf = a2_base + bsel * buf_bytes;
+        mbar_wait(&a2_empty[bsel], (static_cast<uint32_t>(n2 >> 1) & 1u) ^ 1u);   // the MMA of view n2 - 2 has read this buffer
         // ---- pack: this row's half of relu6(bn(gain * conv1d_1)) as fp16 into the row buffer ----
         if (pack_on) {
           uint32_t va[32];
@@ -915,17 +958,19 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const int cg = ch0 + cc * 4 + k;
-                *reinterpret_cast<uint4*>(raw_base + (cg >> 3) * A_SLAB_BYTES + swz_off(row, cg & 7)) =
+                *reinterpret_cast<uint4*>(buf + (cg >> 3) * A_SLAB_BYTES + swz_off(row, cg & 7)) =
                     pack8_relu6(va + 8 * k, s_sh1 + cg * 8, gain);
               }
             }
           }
         }
         asm volatile("bar.sync 2, %0;" ::"n"(FUSE_MID_WARPS * 32) : "memory");   // all rows of this view are in the buffer
-        mbar_wait(a2_empty, (static_cast<uint32_t>(n2) & 1u) ^ 1u);
-        // ---- depthwise FIR: rows 8 fg .. 8 fg + 7 of chunk fc of K slab fkb (rows 126, 127 are never stored) ----
+        // ---- depthwise FIR, in place: rows 8 fg .. 8 fg + 7 of chunk fc of K slab fkb (rows 126, 127 are never stored
+        //      to global memory).  Output row r overwrites buffer row r, which the thread of the previous run still
+        //      needs as its taps: every thread loads its 10 rows first, a barrier, then the stores. ----
+        uint4 o[8];
         if (fir_on) {
-          const uint8_t* rsl = raw_base + fkb * A_SLAB_BYTES + (8 * fg) * ROW_BYTES;
+          const uint8_t* rsl = buf + fkb * A_SLAB_BYTES + (8 * fg) * ROW_BYTES;
           const int cg = fkb * 8 + fc;
           const uint4 k0 = *reinterpret_cast<const uint4*>(s_taps + cg * 8);
           const uint4 k1 = *reinterpret_cast<const uint4*>(s_taps + p.c0 + cg * 8);
@@ -933,14 +978,19 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
           uint4 x[10];
 #pragma unroll
           for (int r = 0; r < 10; ++r) x[r] = lds128(rsl + r * ROW_BYTES + ((fc ^ (r & 7)) << 4));
-          uint8_t* dst = a2_base + fkb * A_SLAB_BYTES + (8 * fg) * ROW_BYTES;
 #pragma unroll
-          for (int r = 0; r < 8; ++r)
-            *reinterpret_cast<uint4*>(dst + r * ROW_BYTES + ((fc ^ r) << 4)) = fir3(x[r], x[r + 1], x[r + 2], k0, k1, k2);
+          for (int r = 0; r < 8; ++r) o[r] = fir3(x[r], x[r + 1], x[r + 2], k0, k1, k2);
+          asm volatile("" ::"r"(o[0].x), "r"(o[1].x), "r"(o[2].x), "r"(o[3].x), "r"(o[4].x), "r"(o[5].x), "r"(o[6].x),
+                       "r"(o[7].x) : "memory");
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(FUSE_MID_WARPS * 32) : "memory");   // every tap has been read
+        if (fir_on) {
+          uint8_t* dst = buf + fkb * A_SLAB_BYTES + (8 * fg) * ROW_BYTES;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) *reinterpret_cast<uint4*>(dst + r * ROW_BYTES + ((fc ^ r) << 4)) = o[r];
         }
         fence_proxy_async_smem();
-        mbar_arrive(a2_full);
-        asm volatile("bar.sync 2, %0;" ::"n"(FUSE_MID_WARPS * 32) : "memory");   // the buffer may be overwritten
+        mbar_arrive(&a2_full[bsel]);
       }
       tc_fence_before();
       mbar_arrive(&acc1_empty[s1]);
@@ -996,6 +1046,8 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
       const uint32_t a1 = umma_desc_lo(smem_u32(a1_base)), w1 = umma_desc_lo(smem_u32(w1_base));
       const uint32_t w2 = umma_desc_lo(smem_u32(w2_base)), a2 = umma_desc_lo(smem_u32(a2_base));
       const uint32_t w1_slab = static_cast<uint32_t>(p.c0) * (ROW_BYTES >> 4), w2_slab = static_cast<uint32_t>(p.c1) * (ROW_BYTES >> 4);
+      const uint32_t a2_buf_lo = static_cast<uint32_t>(nkb2) * (A_SLAB_BYTES >> 4);
+      const uint32_t a2_empty0 = smem_u32(a2_empty), acc2_full0 = smem_u32(acc2_full);
       mbar_wait(w_full, 0);
       uint32_t ph_a1 = 0;
       auto issue_conv1 = [&](int i) {                            // conv1d_1 GEMM of this CTA's i-th unit
@@ -1024,21 +1076,13 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
           const int s2 = n2 & 1;
           const uint32_t ph2 = static_cast<uint32_t>(n2 >> 1) & 1u;
           mbar_wait(&acc2_empty[s2], ph2 ^ 1u);
-          mbar_wait(a2_full, static_cast<uint32_t>(n2) & 1u);
+          mbar_wait(&a2_full[s2], ph2);                          // A buffer n2 % 2 (filled in place by the middle warps)
           tc_fence_after();
           const uint32_t d = tmem_base + acc2_col0 + static_cast<uint32_t>(s2 * p.c1);
-          if (elect_one()) {
-            uint32_t a = a2, w = w2;
-            for (int kb = 0; kb < nkb2; ++kb, a += A_SLAB_BYTES >> 4, w += w2_slab) {
-              umma_f16_lo(d, a, w, idesc2, kb != 0 ? 1u : 0u);
-              umma_f16_lo(d, a + 2, w + 2, idesc2, 1u);
-              umma_f16_lo(d, a + 4, w + 4, idesc2, 1u);
-              umma_f16_lo(d, a + 6, w + 6, idesc2, 1u);
-            }
-            umma_commit(a2_empty);
-            umma_commit(&acc2_full[s2]);
-          }
-          __syncwarp();
+          uint32_t a = a2 + static_cast<uint32_t>(s2) * a2_buf_lo, w = w2;
+          for (int kb = 0; kb < nkb2; ++kb, a += A_SLAB_BYTES >> 4, w += w2_slab)
+            umma_slab4_commit(d, a, w, idesc2, kb != 0 ? 1u : 0u, kb == nkb2 - 1 ? a2_empty0 + 8u * s2 : 0u,
+                              kb == nkb2 - 1 ? acc2_full0 + 8u * s2 : 0u);
         }
       }
     }
@@ -1241,9 +1285,31 @@ int launch_tc_gemm(kws_handle* h, GemmParams& p, cudaStream_t st) {
   }
   static const int knockout = [] { const char* e = getenv("KWS_KNOCKOUT"); return e ? atoi(e) : 0; }();
   p.knockout = knockout;
+  static const int trace_block = [] { const char* e = getenv("KWS_TRACE"); return e ? atoi(e) : -1; }();
+  static int trace_launches = 0;
+  const bool tracing = MODE != 0 && trace_block == p.block_index && ++trace_launches == 2;   // a warmed-up launch
+  p.trace = nullptr;
+  if (tracing) {
+    cudaMalloc(&p.trace, sizeof(unsigned long long) * TRACE_EVENTS * TRACE_ROLES);
+    cudaMemset(p.trace, 0, sizeof(unsigned long long) * TRACE_EVENTS * TRACE_ROLES);
+  }
   KWS_T0(h, MODE == 0 ? KC_CONV1 : KC_BLOCK0 + p.block_index, st);
   tc_gemm_kernel<MODE><<<grid, Roles<MODE>::THREADS, lay.total, st>>>(p);
   KWS_T1(h, st);
+  if (tracing) {                                                 // profiling aid only: synchronises and writes a file
+    std::vector<unsigned long long> ev(static_cast<size_t>(TRACE_EVENTS) * TRACE_ROLES);
+    cudaDeviceSynchronize();
+    cudaMemcpy(ev.data(), p.trace, ev.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(p.trace);
+    if (FILE* f = fopen("gpurun_out/trace.bin", "wb")) {
+      fwrite(ev.data(), sizeof(unsigned long long), ev.size(), f);
+      fclose(f);
+    }
+    fprintf(stderr, "kws trace: block %d cin %d cout %d stride %d num_kb %d a_stages %d raw_stages %d b_resident %d b_stages %d "
+                    "n_split %d acc_stages %d tiles %d grid %d\n",
+            p.block_index, p.cin, p.cout, p.stride, p.num_kb, p.a_stages, p.raw_stages, p.b_resident, p.b_stages, p.n_split,
+            p.acc_stages, p.num_tiles, grid);
+  }
   if (debug_sync() && cudaDeviceSynchronize() != cudaSuccess)
     return fail(h, KWS_ECUDA, "tc_gemm_kernel<" + std::to_string(MODE) + "> cin " + std::to_string(p.cin) + " cout " +
                                   std::to_string(p.cout) + " rows_out " + std::to_string(p.rows_out) + " stages a/b/raw " +

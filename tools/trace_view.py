@@ -2,12 +2,11 @@
 import sys
 import numpy as np
 EV = 4096
-ROLES = {0: "epi", 1: "mma", 2: "raw", 3: "prod0", 4: "prod1"}
+ROLES = {0: "epi", 1: "mma", 2: "raw", 3: "prod"}
 NAMES = {0: {1: "wait_acc_full", 2: "got_acc_full", 3: "done"},
          1: {1: "wait_acc_empty", 2: "got_acc_empty", 3: "got_a_full", 4: "issued", 5: "fenced", 6: "mma_issued", 7: "committed"},
          2: {1: "wait_stage_empty", 2: "got_stage_empty"},
-         3: {1: "wait_raw_full", 2: "got_raw_full", 3: "fir_done", 4: "bar_done", 5: "arrived"},
-         4: {1: "wait_raw_full", 2: "got_raw_full", 3: "fir_done", 4: "bar_done", 5: "arrived"}}
+         3: {1: "wait_raw_full", 2: "got_raw_full", 3: "fir_done", 4: "got_a_empty", 5: "arrived"}}
 d = np.fromfile(sys.argv[1], dtype=np.uint64).reshape(-1, EV)
 lo, hi = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (200, 260)
 t0 = None
