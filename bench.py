@@ -186,6 +186,9 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL prints its version banner on stdout when NCCL_DEBUG is set in the environment; stdout carries the
+        # one JSON line of the contract, so NCCL's log goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     dev = torch.device(f"cuda:{local}")
     B, V = args.batch, 8
