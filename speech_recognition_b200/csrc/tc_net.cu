@@ -795,16 +795,17 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
 //   warps 0-7  middle  : acc1 -> gain, shift, ReLU6, fp16 -> row buffer | FIR -> A2 slabs; two warps per TMEM
 //                        lane quarter, each on half of the channels (this stage is issue/latency-bound: it
 //                        needs two warps per scheduler to hide its own instruction latencies)
-//   warps 8-15 output  : acc2 -> shift, ReLU6, fp16 -> swizzled box -> TMA store; two warps per lane quarter on
-//                        alternate 64-column chunks
-//   warp  16   MMA     : conv1d_1 GEMM (K = 80) once per (clip, view group, tile), pointwise GEMM per view
-//   warp  17   weights : one bulk copy of both weight images (resident)
-//   warps 18-21 window : Conv1Producer (waveform window one tile ahead, swizzled A1 fill)
+//   warps 8-11 output  : acc2 -> shift, ReLU6, fp16 -> swizzled box -> TMA store
+//   warp  12   MMA     : one bulk copy of both weight images (resident); conv1d_1 GEMM (K = 80) once per
+//                        (clip, view group, tile), pointwise GEMM per view
+//   warps 13-15 window : Conv1Producer (waveform window one tile ahead, swizzled A1 fill)
 // ------------------------------------------------------------------------------------------------
 constexpr int FUSE_ROWS = TILE_M - 2;                            // block-1 rows per tile
-constexpr int FUSE_MID_WARPS = 8, FUSE_OUT_WARP0 = 8, FUSE_OUT_WARPS = 4, FUSE_MMA_WARP = 12, FUSE_W_WARP = 13, FUSE_PROD_WARP0 = 14;
-constexpr int FUSE_PROD_THREADS = 128;
-constexpr int FUSE_THREADS = 32 * FUSE_PROD_WARP0 + FUSE_PROD_THREADS;   // 704
+// 16 warps = 512 threads: the register file then allows 128 registers per thread (the middle warps are the
+// critical role and spill at 96)
+constexpr int FUSE_MID_WARPS = 8, FUSE_OUT_WARP0 = 8, FUSE_OUT_WARPS = 4, FUSE_MMA_WARP = 12, FUSE_PROD_WARP0 = 13;
+constexpr int FUSE_PROD_THREADS = 96;
+constexpr int FUSE_THREADS = 32 * FUSE_PROD_WARP0 + FUSE_PROD_THREADS;   // 512
 
 struct alignas(64) FusedParams {
   CUtensorMap tmap_out;      // block-1 output, 3-D [clip-views, t2, c1], box [64 ch, 32 rows, 1], 128-byte swizzle
@@ -949,18 +950,24 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
         mbar_wait(&a2_empty[bsel], (static_cast<uint32_t>(n2 >> 1) & 1u) ^ 1u);   // the MMA of view n2 - 2 has read this buffer
         // ---- pack: this row's half of relu6(bn(gain * conv1d_1)) as fp16 into the row buffer ----
         if (pack_on) {
-          uint32_t va[32];
+          // both TMEM loads of this row are in flight before either is consumed (the TMEM read port, 64 B / cycle
+          // per SM and shared with the output warps, is the scarcest resource of this kernel)
+          uint32_t va[32], vb[32];
+          tmem_ld32(taddr, va);
+          if (nchw > 4) tmem_ld32(taddr + 32, vb);
+          tmem_ld_wait();
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            if (cc * 4 < nchw) {
-              tmem_ld32(taddr + cc * 32, va);
-              tmem_ld_wait();
+          for (int k = 0; k < 4; ++k) {
+            const int cg = ch0 + k;
+            *reinterpret_cast<uint4*>(buf + (cg >> 3) * A_SLAB_BYTES + swz_off(row, cg & 7)) =
+                pack8_relu6(va + 8 * k, s_sh1 + cg * 8, gain);
+          }
+          if (nchw > 4) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int cg = ch0 + cc * 4 + k;
-                *reinterpret_cast<uint4*>(buf + (cg >> 3) * A_SLAB_BYTES + swz_off(row, cg & 7)) =
-                    pack8_relu6(va + 8 * k, s_sh1 + cg * 8, gain);
-              }
+            for (int k = 0; k < 4; ++k) {
+              const int cg = ch0 + 4 + k;
+              *reinterpret_cast<uint4*>(buf + (cg >> 3) * A_SLAB_BYTES + swz_off(row, cg & 7)) =
+                  pack8_relu6(vb + 8 * k, s_sh1 + cg * 8, gain);
             }
           }
         }
@@ -1048,6 +1055,13 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
       const uint32_t w1_slab = static_cast<uint32_t>(p.c0) * (ROW_BYTES >> 4), w2_slab = static_cast<uint32_t>(p.c1) * (ROW_BYTES >> 4);
       const uint32_t a2_buf_lo = static_cast<uint32_t>(nkb2) * (A_SLAB_BYTES >> 4);
       const uint32_t a2_empty0 = smem_u32(a2_empty), acc2_full0 = smem_u32(acc2_full);
+      if (lane == 0) {                                           // both weight images, once (resident)
+        const uint32_t b1 = 2u * p.c0 * ROW_BYTES, b2 = static_cast<uint32_t>(nkb2) * p.c1 * ROW_BYTES;
+        mbar_arrive_expect_tx(w_full, b1 + b2);
+        for (uint32_t o = 0; o < b1; o += 16384) bulk_g2s(w1_base + o, p.w1_img + o, min(16384u, b1 - o), w_full);
+        for (uint32_t o = 0; o < b2; o += 16384) bulk_g2s(w2_base + o, p.w2_img + o, min(16384u, b2 - o), w_full);
+      }
+      __syncwarp();
       mbar_wait(w_full, 0);
       uint32_t ph_a1 = 0;
       auto issue_conv1 = [&](int i) {                            // conv1d_1 GEMM of this CTA's i-th unit
@@ -1085,14 +1099,6 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
                               kb == nkb2 - 1 ? acc2_full0 + 8u * s2 : 0u);
         }
       }
-    }
-  } else if (warp == FUSE_W_WARP) {
-    // =========================== weights (resident) ===========================
-    if (lane == 0) {
-      const uint32_t b1 = 2u * p.c0 * ROW_BYTES, b2 = static_cast<uint32_t>(nkb2) * p.c1 * ROW_BYTES;
-      mbar_arrive_expect_tx(w_full, b1 + b2);
-      for (uint32_t o = 0; o < b1; o += 16384) bulk_g2s(w1_base + o, p.w1_img + o, min(16384u, b1 - o), w_full);
-      for (uint32_t o = 0; o < b2; o += 16384) bulk_g2s(w2_base + o, p.w2_img + o, min(16384u, b2 - o), w_full);
     }
   } else {
     // =========================== waveform window producers ===========================
