@@ -901,8 +901,8 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
       mbar_init(a1_full, FUSE_PROD_THREADS);
       mbar_init(a1_empty, 1);
       for (int i = 0; i < 2; ++i) {
-        mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], FUSE_MID_WARPS * 32);
-        mbar_init(&a2_full[i], FUSE_MID_WARPS * 32); mbar_init(&a2_empty[i], 1);
+        mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], FUSE_MID_WARPS);
+        mbar_init(&a2_full[i], FUSE_MID_WARPS); mbar_init(&a2_empty[i], 1);
         mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], FUSE_OUT_WARPS * 32);
       }
       mbar_init(w_full, 1);
@@ -918,11 +918,19 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t acc2_col0 = 2u * p.c0;
 
+  // Each CTA works on a contiguous range of units (tile j of view group g of clip b, j fastest): the (b, g, j) of
+  // the next unit is an increment (the divisions of decode() were ~700 cycles of the middle warps' chain per unit),
+  // and the twelve units of a clip read its waveform from the same SM.
+  const int u0 = static_cast<int>(static_cast<long long>(p.num_units) * blockIdx.x / gridDim.x);
+  const int u1 = static_cast<int>(static_cast<long long>(p.num_units) * (blockIdx.x + 1) / gridDim.x);
   auto decode = [&](int unit, int& b, int& g, int& j) {
     j = unit % p.blocks_per_view;
     const int ug = unit / p.blocks_per_view;
     g = ug % p.vg.n_groups;
     b = ug / p.vg.n_groups;
+  };
+  auto advance = [&](int& b, int& g, int& j) {                   // (b, g, j) of unit + 1
+    if (++j == p.blocks_per_view) { j = 0; if (++g == p.vg.n_groups) { g = 0; ++b; } }
   };
 
   if (warp < FUSE_MID_WARPS) {
@@ -933,9 +941,15 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
     const int fkb = tid >> 7, ftg = tid & 127;                   // FIR phase: K slab and (chunk, 8-row run) of this thread
     const int fc = ftg & 7, fg = ftg >> 3;
     const uint32_t buf_bytes = static_cast<uint32_t>(nkb2) * A_SLAB_BYTES;
+    // this thread's depthwise taps never change (fkb < nkb2 for every FIR thread that is ever on)
+    const int fcg = (fkb < nkb2 ? fkb : 0) * 8 + fc;
+    const uint4 k0 = *reinterpret_cast<const uint4*>(s_taps + fcg * 8);
+    const uint4 k1 = *reinterpret_cast<const uint4*>(s_taps + p.c0 + fcg * 8);
+    const uint4 k2 = *reinterpret_cast<const uint4*>(s_taps + 2 * p.c0 + fcg * 8);
     int n2 = 0, i = 0;
-    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++i) {
-      int b, g, j; decode(unit, b, g, j);
+    int b = 0, g = 0, j = 0;
+    if (u0 < u1) decode(u0, b, g, j);
+    for (int unit = u0; unit < u1; ++unit, ++i, advance(b, g, j)) {
       const int s1 = i & 1;
       mbar_wait(&acc1_full[s1], static_cast<uint32_t>(i >> 1) & 1u);
       tc_fence_after();
@@ -950,24 +964,18 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
         mbar_wait(&a2_empty[bsel], (static_cast<uint32_t>(n2 >> 1) & 1u) ^ 1u);   // the MMA of view n2 - 2 has read this buffer
         // ---- pack: this row's half of relu6(bn(gain * conv1d_1)) as fp16 into the row buffer ----
         if (pack_on) {
-          // both TMEM loads of this row are in flight before either is consumed (the TMEM read port, 64 B / cycle
-          // per SM and shared with the output warps, is the scarcest resource of this kernel)
-          uint32_t va[32], vb[32];
-          tmem_ld32(taddr, va);
-          if (nchw > 4) tmem_ld32(taddr + 32, vb);
-          tmem_ld_wait();
+          uint32_t va[32];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int cg = ch0 + k;
-            *reinterpret_cast<uint4*>(buf + (cg >> 3) * A_SLAB_BYTES + swz_off(row, cg & 7)) =
-                pack8_relu6(va + 8 * k, s_sh1 + cg * 8, gain);
-          }
-          if (nchw > 4) {
+          for (int cc = 0; cc < 2; ++cc) {
+            if (cc * 4 < nchw) {
+              tmem_ld32(taddr + cc * 32, va);
+              tmem_ld_wait();
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int cg = ch0 + 4 + k;
-              *reinterpret_cast<uint4*>(buf + (cg >> 3) * A_SLAB_BYTES + swz_off(row, cg & 7)) =
-                  pack8_relu6(vb + 8 * k, s_sh1 + cg * 8, gain);
+              for (int k = 0; k < 4; ++k) {
+                const int cg = ch0 + cc * 4 + k;
+                *reinterpret_cast<uint4*>(buf + (cg >> 3) * A_SLAB_BYTES + swz_off(row, cg & 7)) =
+                    pack8_relu6(va + 8 * k, s_sh1 + cg * 8, gain);
+              }
             }
           }
         }
@@ -978,10 +986,6 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
         uint4 o[8];
         if (fir_on) {
           const uint8_t* rsl = buf + fkb * A_SLAB_BYTES + (8 * fg) * ROW_BYTES;
-          const int cg = fkb * 8 + fc;
-          const uint4 k0 = *reinterpret_cast<const uint4*>(s_taps + cg * 8);
-          const uint4 k1 = *reinterpret_cast<const uint4*>(s_taps + p.c0 + cg * 8);
-          const uint4 k2 = *reinterpret_cast<const uint4*>(s_taps + 2 * p.c0 + cg * 8);
           uint4 x[10];
 #pragma unroll
           for (int r = 0; r < 10; ++r) x[r] = lds128(rsl + r * ROW_BYTES + ((fc ^ (r & 7)) << 4));
@@ -997,10 +1001,12 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
           for (int r = 0; r < 8; ++r) *reinterpret_cast<uint4*>(dst + r * ROW_BYTES + ((fc ^ r) << 4)) = o[r];
         }
         fence_proxy_async_smem();
-        mbar_arrive(&a2_full[bsel]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a2_full[bsel]);              // one arrival per warp
       }
       tc_fence_before();
-      mbar_arrive(&acc1_empty[s1]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc1_empty[s1]);
     }
   } else if (warp < FUSE_MMA_WARP) {
     // =========================== output: acc2 -> BN shift, ReLU6 -> TMA store ===========================
@@ -1011,8 +1017,9 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
     uint8_t* row_base = box + lane * ROW_BYTES;
     int n2 = 0;
     if (lane == 0) { tma_prefetch_desc(&p.tmap_out); tma_prefetch_desc(&p.tmap_out30); }
-    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
-      int b, g, j; decode(unit, b, g, j);
+    int b = 0, g = 0, j = 0;
+    if (u0 < u1) decode(u0, b, g, j);
+    for (int unit = u0; unit < u1; ++unit, advance(b, g, j)) {
       const int row0 = j * FUSE_ROWS + q * 32;                   // first block-1 row of this warp's box
       for (int mem = p.vg.start[g]; mem < p.vg.start[g + 1]; ++mem, ++n2) {
         const int s2 = n2 & 1;
@@ -1082,10 +1089,11 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
         __syncwarp();
       };
       int i = 0, n2 = 0;
-      if (static_cast<int>(blockIdx.x) < p.num_units) issue_conv1(0);
-      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++i) {
-        if (unit + static_cast<int>(gridDim.x) < p.num_units) issue_conv1(i + 1);   // next tile's conv1d_1 runs under this tile's views
-        int b, g, j; decode(unit, b, g, j);
+      if (u0 < u1) issue_conv1(0);
+      int b = 0, g = 0, j = 0;
+      if (u0 < u1) decode(u0, b, g, j);
+      for (int unit = u0; unit < u1; ++unit, ++i, advance(b, g, j)) {
+        if (unit + 1 < u1) issue_conv1(i + 1);                   // next tile's conv1d_1 runs under this tile's views
         for (int mem = p.vg.start[g]; mem < p.vg.start[g + 1]; ++mem, ++n2) {
           const int s2 = n2 & 1;
           const uint32_t ph2 = static_cast<uint32_t>(n2 >> 1) & 1u;
@@ -1113,13 +1121,13 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
       x = p.wav + static_cast<size_t>(b) * L;
       return Conv1Producer::make(p.vg.shift[g], j * FUSE_ROWS, min(TILE_M, p.t1 - j * FUSE_ROWS));
     };
-    int unit = blockIdx.x;
-    if (unit < p.num_units) { cur = describe(unit); Conv1Producer::load(cur, x, ptid, qd); }
-    for (; unit < p.num_units; unit += gridDim.x) {
+    int unit = u0;
+    if (unit < u1) { cur = describe(unit); Conv1Producer::load(cur, x, ptid, qd); }
+    for (; unit < u1; ++unit) {
       __half* win = reinterpret_cast<__half*>(win_base + buf * CONV1_WIN_BYTES);
       Conv1Producer::store(cur, ptid, qd, win);
-      const int next = unit + gridDim.x;
-      if (next < p.num_units) { nxt = describe(next); Conv1Producer::load(nxt, x, ptid, qd); }
+      const int next = unit + 1;
+      if (next < u1) { nxt = describe(next); Conv1Producer::load(nxt, x, ptid, qd); }
       asm volatile("bar.sync 1, %0;" ::"n"(FUSE_PROD_THREADS) : "memory");    // window complete
       mbar_wait(a1_empty, pe ^ 1u);
       Conv1Producer::fill_slabs(a1_base, ptid, win, cur.rows);
