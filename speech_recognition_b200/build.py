@@ -15,6 +15,8 @@ LIB = os.path.join(HERE, "libkws.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+if os.environ.get("KWS_PROFILE_BUILD", "0") not in ("", "0"):       # knockout switches + event trace in the block kernel
+    NVCC_FLAGS.append("-DKWS_PROFILE_BUILD=1")
 
 
 def _nvcc():

@@ -37,11 +37,20 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 
+// Profiling build (KWS_PROFILE_BUILD=1 python -m speech_recognition_b200.build --force): compiles the
+// KWS_KNOCKOUT switches and the KWS_TRACE event log into the block kernel.  The production build
+// carries neither (the trace call sites alone cost ~20 instructions per K slab on the producers' chain).
+#ifndef KWS_PROFILE_BUILD
+#define KWS_PROFILE_BUILD 0
+#endif
+
 namespace kws {
 
 using namespace tc;
 
 namespace {
+
+constexpr bool kProfile = KWS_PROFILE_BUILD != 0;
 
 // Warp roles depend on the layer type: the dw_pw blocks are fed by 8 depthwise producer warps and
 // drained by 4 epilogue warps; conv1d_1 is bound by its epilogue (one pass per TTA view of a
@@ -371,6 +380,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const fl
 // only CTA 0 writes, one thread per role.  p.trace == nullptr (always, unless KWS_TRACE is set) disables it.
 constexpr int TRACE_EVENTS = 4096, TRACE_ROLES = 4;
 __device__ __forceinline__ void trace_ev(unsigned long long* trace, int role, int& cnt, int ev, int idx) {
+  if constexpr (!kProfile) return;
   if (trace != nullptr && blockIdx.x == 0 && cnt < TRACE_EVENTS) {
     const unsigned long long c = static_cast<unsigned long long>(clock64());
     trace[role * TRACE_EVENTS + cnt++] = (static_cast<unsigned long long>(ev) << 56) |
@@ -479,7 +489,7 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
         row0 = tile * TILE_M + quarter * 32;
       }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * p.ncta);
-      if (p.knockout & 8) m1 = m0;
+      if (kProfile && (p.knockout & 8)) m1 = m0;
       for (int mem = m0; mem < m1; ++mem) {
         const float gain = kConv1 ? p.vg.gain[mem] : 1.0f;
         const int rv = kConv1 ? rv0 + p.vg.view[mem] : 0;
@@ -505,7 +515,7 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && !(p.knockout & 1)) {
+          if (lane == 0 && !(kProfile && (p.knockout & 1))) {
             if (kConv1) tma_store_3d(&p.tmap_out, c0, row0, rv, box);
             else if (tail) tma_store_2d(&p.tmap_tail, col0 + c0, row0, box);
             else tma_store_2d(&p.tmap_out, col0 + c0, row0, box);
@@ -538,7 +548,7 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
       const int num_kb = ((p.num_kb) + zi), n_halves = ((p.n_halves) + zi), last_ksteps = ((p.last_ksteps) + zi);
       const int n_inst = ((p.n_inst) + zi), ncta = ((p.ncta) + zi), b_stages = ((p.b_stages) + zi), acc_stages = ((p.acc_stages) + zi);
       const int num_tiles = ((p.num_tiles) + zi), tstep = ((tstride) + zi);
-      const bool resident = ((p.b_resident) + zi) != 0, ko_mma = ((p.knockout & 4) + zi) != 0;
+      const bool resident = ((p.b_resident) + zi) != 0, ko_mma = kProfile && ((p.knockout & 4) + zi) != 0;
       const uint32_t tmem0 = ((tmem_base) + zi);
       int sa = 0; uint32_t pa = 0; int sb = 0; uint32_t pb = 0; int acc = 0; uint32_t acc_phase = 0;
       int tcnt = 0, tn = 0;
@@ -683,7 +693,7 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
           trace_ev(trace, 2, tcnt, 1, tn);
           mbar_wait(&raw_empty[rs], pr ^ 1);
           trace_ev(trace, 2, tcnt, 2, tn++);
-          if (p.knockout & 16) { mbar_arrive(&raw_full[rs]); if (++rs == p.raw_stages) { rs = 0; pr ^= 1; } continue; }
+          if (kProfile && (p.knockout & 16)) { mbar_arrive(&raw_full[rs]); if (++rs == p.raw_stages) { rs = 0; pr ^= 1; } continue; }
           mbar_arrive_expect_tx(&raw_full[rs], static_cast<uint32_t>(p.raw_stage_bytes));
           uint8_t* dst = raw_base + rs * p.raw_stage_bytes;
           for (int bx = 0; bx < p.n_boxes; ++bx)
@@ -729,7 +739,7 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
       const int raw_stages = p.raw_stages + zi, a_stages = p.a_stages + zi, num_kb = p.num_kb + zi, cin = p.cin + zi;
       const int num_tiles = p.num_tiles + zi, tstep = tstride + zi;
       const uint32_t raw_stage_bytes = static_cast<uint32_t>(p.raw_stage_bytes) + z, a_stage_bytes = static_cast<uint32_t>(p.a_stage_bytes) + z;
-      const bool ko_fir = ((p.knockout & 2) + zi) != 0;
+      const bool ko_fir = kProfile && ((p.knockout & 2) + zi) != 0;
       const int c = ptid & 7;
       int rs = 0, sa = 0, par = 0; uint32_t pr = 0, pa = 0;
       int tcnt = 0, tn = 0;
@@ -1297,11 +1307,16 @@ int launch_tc_gemm(kws_handle* h, GemmParams& p, cudaStream_t st) {
     const int rc = make_tensor_map(h, &p.tmap_tail, p.out_act, p.cout, p.out_rows, 1, 32, false, 32);
     if (rc) return rc;
   }
-  static const int knockout = [] { const char* e = getenv("KWS_KNOCKOUT"); return e ? atoi(e) : 0; }();
+  static const int knockout = [] {
+    const char* e = getenv("KWS_KNOCKOUT");
+    if ((e || getenv("KWS_TRACE")) && !kProfile)
+      fprintf(stderr, "kws: KWS_KNOCKOUT / KWS_TRACE need a profiling build (KWS_PROFILE_BUILD=1 python -m speech_recognition_b200.build --force)\n");
+    return e && kProfile ? atoi(e) : 0;
+  }();
   p.knockout = knockout;
   static const int trace_block = [] { const char* e = getenv("KWS_TRACE"); return e ? atoi(e) : -1; }();
   static int trace_launches = 0;
-  const bool tracing = MODE != 0 && trace_block == p.block_index && ++trace_launches == 2;   // a warmed-up launch
+  const bool tracing = kProfile && MODE != 0 && trace_block == p.block_index && ++trace_launches == 2;   // a warmed-up launch
   p.trace = nullptr;
   if (tracing) {
     cudaMalloc(&p.trace, sizeof(unsigned long long) * TRACE_EVENTS * TRACE_ROLES);
