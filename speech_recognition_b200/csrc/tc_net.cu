@@ -468,11 +468,16 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
     int acc = 0; uint32_t acc_phase = 0;
     uint8_t* my_out = out_base + warp * p.out_bufs * OUT_STAGE_BYTES;
     int obuf = 0;
-    const int quarter = warp & 3, c_first = (warp >> 2) * 64;
+    const int quarter = warp & 3;
     constexpr int c_step = 64 * kColGroups;
+    // with an odd number of 64-column chunks (ncta = 160, 192, 320) the two warps of a lane quarter swap the longer
+    // share every tile, so both drain 1.5 / 2.5 chunks per tile on average
+    const int rotate = (!kConv1 && kColGroups == 2 && (((p.ncta + 63) / 64) & 1)) ? 1 : 0;
+    int c_group = warp >> 2;
     if (lane == 0) tma_prefetch_desc(&p.tmap_out);
     int tcnt = 0, tidx = 0;
-    for (int tile = tile0; tile < p.num_tiles; tile += tstride) {
+    for (int tile = tile0; tile < p.num_tiles; tile += tstride, c_group ^= rotate) {
+      const int c_first = c_group * 64;
       if (warp == 0 && lane == 0) trace_ev(trace, 0, tcnt, 1, tidx);
       mbar_wait(&acc_full[acc], acc_phase);
       if (warp == 0 && lane == 0) trace_ev(trace, 0, tcnt, 2, tidx);
