@@ -1247,6 +1247,7 @@ int launch_tc_gemm(kws_handle* h, GemmParams& p, cudaStream_t st) {
     // first CTA touched them).  Preference: smallest split with resident weights, deep raw ring, deep A ring.
     // (The producers fill the rings strictly in order, so any depth >= 2 is valid.)
     static const int force_a = [] { const char* e = getenv("KWS_A_STAGES"); return e ? atoi(e) : 0; }();       // A/B aids
+    static const int force_ob = [] { const char* e = getenv("KWS_OUT_BUFS"); return e ? atoi(e) : 0; }();
     static const int force_r = [] { const char* e = getenv("KWS_RAW_STAGES"); return e ? atoi(e) : 0; }();
     auto fits_f = [&](int a, int b, int r) {
       if ((force_a && a != force_a) || (force_r && r != force_r)) return false;
@@ -1262,18 +1263,24 @@ int launch_tc_gemm(kws_handle* h, GemmParams& p, cudaStream_t st) {
         if (ob_lo == 2) {                                        // narrow layers
           // resident weights first (measured: 192->192 with resident weights and a 2-deep A ring beats streamed
           // weights with a 4-deep A ring by 8 %), then streamed weights with the deepest rings that fit
-          p.out_bufs = 1;                                        // two epilogue warps per lane quarter alternate: one box each
-          if (blocks <= MAX_B_BLOCKS)
-            for (int r = 6; r >= r_min && !chosen; --r)            // TMA prefetch depth matters more than A-ring depth
-              for (int a = 4; a >= 2 && !chosen; --a)
-                if (fits_f(a, blocks, r)) { p.b_resident = 1; chosen = true; }
-          for (int a = 4; a >= 2 && !chosen; --a)
-            for (int res = 1; res >= (resident_only ? 1 : 0) && !chosen; --res) {
-              if (res && blocks > MAX_B_BLOCKS) continue;
-              for (int bs = res ? blocks : b_stream; bs >= (res ? blocks : 2) && !chosen; --bs)
-                for (int r = 6; r >= 2 && !chosen; --r)
-                  if (fits_f(a, bs, r)) { p.b_resident = res; chosen = true; }
-            }
+          // two epilogue warps per lane quarter alternate, so one store box each is enough -- except when the single
+          // accumulator stage of a 320-512-column layer exposes the epilogue (measured: -7 % / -6 % on 256->320 and
+          // 320->384 with two boxes, +15 % on the layers that lose ring depth to them); KWS_OUT_BUFS: A/B aid
+          const int ob_first = force_ob ? force_ob : (p.acc_stages == 1 ? 2 : 1);
+          for (int ob = ob_first == 2 ? 2 : 1; ob >= 1 && !chosen; --ob) {
+            p.out_bufs = ob;
+            if (blocks <= MAX_B_BLOCKS)
+              for (int r = 6; r >= r_min && !chosen; --r)          // TMA prefetch depth matters more than A-ring depth
+                for (int a = 4; a >= 2 && !chosen; --a)
+                  if (fits_f(a, blocks, r)) { p.b_resident = 1; chosen = true; }
+            for (int a = 4; a >= 2 && !chosen; --a)
+              for (int res = 1; res >= (resident_only ? 1 : 0) && !chosen; --res) {
+                if (res && blocks > MAX_B_BLOCKS) continue;
+                for (int bs = res ? blocks : b_stream; bs >= (res ? blocks : 2) && !chosen; --bs)
+                  for (int r = 6; r >= 2 && !chosen; --r)
+                    if (fits_f(a, bs, r)) { p.b_resident = res; chosen = true; }
+              }
+          }
         } else {                                                 // split layers: deep raw ring (HBM/L2 latency) first
           for (int res = 1; res >= (resident_only ? 1 : 0) && !chosen; --res) {
             if (res && blocks > MAX_B_BLOCKS) continue;
