@@ -172,7 +172,7 @@ def run_reference(args):
         "e2e": {"value": best["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------
@@ -186,9 +186,6 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL prints its version banner on stdout when NCCL_DEBUG is set in the environment; stdout carries the
-        # one JSON line of the contract, so NCCL's log goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     dev = torch.device(f"cuda:{local}")
     B, V = args.batch, 8
@@ -335,14 +332,33 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_rate(views, seconds_target=15.0)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     eng.close()
 
 
+def _claim_stdout():
+    """stdout carries exactly one JSON line (the contract).  Libraries print there too (NCCL's version banner when
+    NCCL_DEBUG is set in the environment), so file descriptor 1 is pointed at stderr for everything else and the
+    JSON line is written through a private duplicate of the original stdout."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+_JSON_OUT = sys.stdout
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
