@@ -157,7 +157,7 @@ def run_reference(args):
     t0 = time.perf_counter()
     res = []
     for _ in range(max(1, min(args.steps, 3))):
-        res.append(cpu_reference_rate(TTA_8, seconds_target=15.0))
+        res.append(cpu_reference_rate(TTA_8, seconds_target=args.ref_seconds))
     best = max(res, key=lambda r: r["value"])
     line = {
         "impl": "reference", "metric": "1s-clips/sec (aug+feat+fwd, 8x TTA)", "value": best["value"],
@@ -368,6 +368,7 @@ def main():
     ap.add_argument("--max-rows", type=int, default=32768, help="clip-views per internal chunk")
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-seconds", type=float, default=15.0, help="--impl reference: CPU seconds per step (bounded sample)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
