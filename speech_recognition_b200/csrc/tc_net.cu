@@ -1295,10 +1295,12 @@ int launch_tc_gemm(kws_handle* h, GemmParams& p, cudaStream_t st) {
         }
       }
     };
-    // Measured (profiles/): the 2-way split pays for the stride-1 wide layers (320->320, 384->384, 512->512); the
-    // stride-2 ones have double-size raw stages, lose their TMA prefetch depth to the resident weights and get
-    // slower, and 3/4-way splits re-read the raw rows more than they save in weight traffic.
-    static const int max_split = [] { const char* e = getenv("KWS_MAX_SPLIT"); return e ? atoi(e) : 2; }();   // A/B aid
+    // Column split of the wide layers (cout > 256) over 2 adjacent CTAs: resident weight slices and two accumulator
+    // stages, but the A operand is produced once per slice.  It paid (-12 / -7 / -6 % on 320->320, 384->384, 512->512)
+    // while the MMA issue and the epilogue were slow; with this round's pipeline the unsplit form -- streamed weights,
+    // one accumulator stage, two store boxes per epilogue warp -- is 2-7 % faster on those three layers and the
+    // stride-2 ones, so the split is off by default (KWS_MAX_SPLIT=2, plus KWS_SPLIT_S2=1 for the stride-2 layers, re-enables it for A/B runs).
+    static const int max_split = [] { const char* e = getenv("KWS_MAX_SPLIT"); return e ? atoi(e) : 1; }();   // A/B aid
     static const bool split_s2 = [] { const char* e = getenv("KWS_SPLIT_S2"); return e && e[0] == '1'; }();           // A/B aid
     if (p.cout <= 256 || max_split < 2 || (MODE != 1 && !split_s2)) {
       search(1, 1, false, 2);                                    // weights resident when they fit, else streamed
