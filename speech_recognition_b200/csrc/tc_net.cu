@@ -127,6 +127,10 @@ struct alignas(64) GemmParams {
                             // CTA c works on columns [(c % n_split) * ncta, +ncta) of tiles c / n_split, + grid / n_split, ...
                             // so that its slice of the weights stays resident and two accumulators fit in TMEM
   int n_inst, n_halves;     // ncta = n_inst * n_halves, n_inst <= 256
+  int two_pass;             // dw_pw, n_halves == 2: the A ring holds every K slab of a tile and the MMAs run half by half
+                            // (all slabs for columns [0, n_inst), then all slabs for [n_inst, 2 n_inst)), each half into
+                            // its own TMEM region with its own full / empty barrier: the epilogue of one half overlaps the
+                            // MMAs of the other half / the next tile although two whole accumulators do not fit in TMEM
   int out_bufs;             // store boxes per epilogue warp (2, or 1 when shared memory is short)
   int a_stage_bytes;        // dw_pw: 16 KB; conv1: 32 KB (both slabs of a tile)
   int raw_stage_bytes, box_rows, n_boxes;
@@ -472,16 +476,13 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
     constexpr int c_step = 64 * kColGroups;
     // with an odd number of 64-column chunks (ncta = 160, 192, 320) the two warps of a lane quarter swap the longer
     // share every tile, so both drain 1.5 / 2.5 chunks per tile on average
-    const int rotate = (!kConv1 && kColGroups == 2 && (((p.ncta + 63) / 64) & 1)) ? 1 : 0;
+    const int n_pass = (!kConv1 && p.two_pass) ? 2 : 1;          // two_pass: one drain per N half
+    const int ncols = n_pass == 2 ? p.n_inst : p.ncta;           // columns per drain
+    const int rotate = (!kConv1 && kColGroups == 2 && (((ncols + 63) / 64) & 1)) ? 1 : 0;
     int c_group = warp >> 2;
     if (lane == 0) tma_prefetch_desc(&p.tmap_out);
     int tcnt = 0, tidx = 0;
-    for (int tile = tile0; tile < p.num_tiles; tile += tstride, c_group ^= rotate) {
-      const int c_first = c_group * 64;
-      if (warp == 0 && lane == 0) trace_ev(trace, 0, tcnt, 1, tidx);
-      mbar_wait(&acc_full[acc], acc_phase);
-      if (warp == 0 && lane == 0) trace_ev(trace, 0, tcnt, 2, tidx);
-      tc_fence_after();
+    for (int tile = tile0; tile < p.num_tiles; tile += tstride) {
       int row0, rv0 = 0, m0 = 0, m1 = 1;                         // first output row of this warp's box; member views
       if (kConv1) {
         const int unit = tile / p.tiles_per_group;
@@ -493,47 +494,58 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
       } else {
         row0 = tile * TILE_M + quarter * 32;
       }
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * p.ncta);
       if (kProfile && (p.knockout & 8)) m1 = m0;
-      for (int mem = m0; mem < m1; ++mem) {
-        const float gain = kConv1 ? p.vg.gain[mem] : 1.0f;
-        const int rv = kConv1 ? rv0 + p.vg.view[mem] : 0;
-        uint32_t va[32], vb[32];
-        if (c_first < p.ncta) tmem_ld32(taddr + c_first, va);
-        for (int c0 = c_first; c0 < p.ncta; c0 += c_step) {
-          const bool tail = p.ncta - c0 < 64;                    // last 32 columns of a 160- or 96-column slice
-          uint8_t* box = my_out + obuf * OUT_STAGE_BYTES;
-          if (lane == 0) {                                       // the store that last used this buffer has read it
-            if (p.out_bufs == 2) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
-          }
-          __syncwarp();
-          tmem_ld_wait();
-          if (!tail) {
-            uint8_t* row_base = box + lane * ROW_BYTES;
-            tmem_ld32(taddr + c0 + 32, vb);
-            epilogue_chunk<kConv1>(va, s_shift + c0, row_base, 0, lane & 7, gain);
+      for (int h = 0; h < n_pass; ++h, c_group ^= rotate) {
+        const int c_first = c_group * 64;
+        const int ai = n_pass == 2 ? h : acc;                    // accumulator barrier / region of this drain
+        const int cbase = n_pass == 2 ? h * ncols : 0;           // first column of this drain inside the CTA's columns
+        if (warp == 0 && lane == 0) trace_ev(trace, 0, tcnt, 1, tidx);
+        mbar_wait(&acc_full[ai], acc_phase);
+        if (warp == 0 && lane == 0) trace_ev(trace, 0, tcnt, 2, tidx);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                               static_cast<uint32_t>(n_pass == 2 ? cbase : acc * p.ncta);
+        for (int mem = m0; mem < m1; ++mem) {
+          const float gain = kConv1 ? p.vg.gain[mem] : 1.0f;
+          const int rv = kConv1 ? rv0 + p.vg.view[mem] : 0;
+          uint32_t va[32], vb[32];
+          if (c_first < ncols) tmem_ld32(taddr + c_first, va);
+          for (int c0 = c_first; c0 < ncols; c0 += c_step) {
+            const bool tail = ncols - c0 < 64;                   // last 32 columns of a 160- or 96-column slice
+            uint8_t* box = my_out + obuf * OUT_STAGE_BYTES;
+            if (lane == 0) {                                     // the store that last used this buffer has read it
+              if (p.out_bufs == 2) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
+            }
+            __syncwarp();
             tmem_ld_wait();
-            if (c0 + c_step < p.ncta) tmem_ld32(taddr + c0 + c_step, va);
-            epilogue_chunk<kConv1>(vb, s_shift + c0 + 32, row_base, 4, lane & 7, gain);
-          } else {
-            epilogue_chunk<kConv1>(va, s_shift + c0, box + lane * (ROW_BYTES / 2), 0, 0, gain);   // dense 64-byte rows
+            if (!tail) {
+              uint8_t* row_base = box + lane * ROW_BYTES;
+              tmem_ld32(taddr + c0 + 32, vb);
+              epilogue_chunk<kConv1>(va, s_shift + cbase + c0, row_base, 0, lane & 7, gain);
+              tmem_ld_wait();
+              if (c0 + c_step < ncols) tmem_ld32(taddr + c0 + c_step, va);
+              epilogue_chunk<kConv1>(vb, s_shift + cbase + c0 + 32, row_base, 4, lane & 7, gain);
+            } else {
+              epilogue_chunk<kConv1>(va, s_shift + cbase + c0, box + lane * (ROW_BYTES / 2), 0, 0, gain);   // dense 64-byte rows
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && !(kProfile && (p.knockout & 1))) {
+              if (kConv1) tma_store_3d(&p.tmap_out, c0, row0, rv, box);
+              else if (tail) tma_store_2d(&p.tmap_tail, col0 + cbase + c0, row0, box);
+              else tma_store_2d(&p.tmap_out, col0 + cbase + c0, row0, box);
+              bulk_commit_group();
+            }
+            obuf = (obuf + 1) & (p.out_bufs - 1);
           }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0 && !(kProfile && (p.knockout & 1))) {
-            if (kConv1) tma_store_3d(&p.tmap_out, c0, row0, rv, box);
-            else if (tail) tma_store_2d(&p.tmap_tail, col0 + c0, row0, box);
-            else tma_store_2d(&p.tmap_out, col0 + c0, row0, box);
-            bulk_commit_group();
-          }
-          obuf = (obuf + 1) & (p.out_bufs - 1);
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[ai]);              // one arrival per warp
+        if (warp == 0 && lane == 0) trace_ev(trace, 0, tcnt, 3, tidx++);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);             // one arrival per warp
-      if (warp == 0 && lane == 0) trace_ev(trace, 0, tcnt, 3, tidx++);
-      if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1; }
+      if (n_pass == 2) acc_phase ^= 1;                           // each half's barrier is used once per tile
+      else if (++acc == p.acc_stages) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) bulk_wait_group_all();
   } else if (warp == MMA_WARP) {
@@ -566,6 +578,40 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
         const uint32_t a_full0 = smem_u32(a_full) + z, a_free0 = smem_u32(a_free) + z, b_full0 = smem_u32(b_full) + z;
         const uint32_t b_empty0 = smem_u32(b_empty) + z, acc_full0 = smem_u32(acc_full) + z;
         int tcnt = 0, tn = 0;
+        if (p.two_pass) {
+          // two passes over the K slabs of a tile, one per N half; a_stages == num_kb, so slab kb of every tile sits in
+          // A slot kb and both passes find it there (the slot is released by the second pass's commit only)
+          uint32_t tile_ph = 0;                                  // every a_full / acc barrier completes once per tile
+          for (int tile = tile0; tile < num_tiles; tile += tstep) {
+            for (int h = 0; h < 2; ++h) {
+              if (lane == 0) trace_ev(trace, 1, tcnt, 1, tn);
+              mbar_wait(&acc_empty[h], tile_ph ^ 1);
+              if (lane == 0) trace_ev(trace, 1, tcnt, 2, tn);
+              const uint32_t d = tmem0 + static_cast<uint32_t>(h * n_inst);
+              for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait_addr(a_full0 + 8u * kb, tile_ph);
+                if (lane == 0) trace_ev(trace, 1, tcnt, 3, tn);
+                const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(kb) * a_stage_lo;
+                uint32_t b_lo, b_bar = 0u;
+                if (!resident) {
+                  mbar_wait_addr(b_full0 + 8u * sb, pb);
+                  b_lo = b_lo0 + static_cast<uint32_t>(sb) * b_block_lo;
+                  b_bar = b_empty0 + 8u * sb;
+                } else {
+                  b_lo = b_lo0 + static_cast<uint32_t>(kb * 2 + h) * b_block_lo;
+                }
+                tc_fence_after();
+                const uint32_t a_bar = h == 1 ? a_free0 + 8u * kb : 0u;
+                if (!ko_mma) umma_slab4_commit(d, a_lo, b_lo, idesc, kb != 0 ? 1u : 0u, b_bar, a_bar);
+                else { if (b_bar) umma_commit_elect(b_bar); if (a_bar) umma_commit_elect(a_bar); }
+                if (!resident) { if (++sb == b_stages) { sb = 0; pb ^= 1; } }
+                if (lane == 0) trace_ev(trace, 1, tcnt, 4, tn++);
+              }
+              umma_commit_elect(acc_full0 + 8u * h);
+            }
+            tile_ph ^= 1;
+          }
+        } else
         for (int tile = tile0; tile < num_tiles; tile += tstep) {
           if (lane == 0) trace_ev(trace, 1, tcnt, 1, tn);
           mbar_wait(&acc_empty[acc], acc_phase ^ 1);
@@ -655,7 +701,9 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
       } else {
         int sb = 0; uint32_t pb = 0;
         for (int tile = tile0; tile < p.num_tiles; tile += tstride) {
-          for (int j = 0; j < blocks_per_tile; ++j) {
+          for (int jj = 0; jj < blocks_per_tile; ++jj) {
+            // block index = kb * n_halves + nh; two_pass consumes them half by half: (nh, kb) order
+            const int j = p.two_pass ? (jj % p.num_kb) * 2 + jj / p.num_kb : jj;
             mbar_wait(&b_empty[sb], pb ^ 1);
             load_block(j, sb, &b_full[sb]);
             if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
@@ -1302,7 +1350,19 @@ int launch_tc_gemm(kws_handle* h, GemmParams& p, cudaStream_t st) {
     // stride-2 ones, so the split is off by default (KWS_MAX_SPLIT=2, plus KWS_SPLIT_S2=1 for the stride-2 layers, re-enables it for A/B runs).
     static const int max_split = [] { const char* e = getenv("KWS_MAX_SPLIT"); return e ? atoi(e) : 1; }();   // A/B aid
     static const bool split_s2 = [] { const char* e = getenv("KWS_SPLIT_S2"); return e && e[0] == '1'; }();           // A/B aid
-    if (p.cout <= 256 || max_split < 2 || (MODE != 1 && !split_s2)) {
+    static const bool no_two_pass = [] { const char* e = getenv("KWS_NO_TWO_PASS"); return e && e[0] == '1'; }();   // A/B aid
+    p.two_pass = 0;
+    if (!no_two_pass && set_split(1) && p.n_halves == 2 && p.num_kb <= MAX_STAGES) {
+      // every K slab of a tile resident in the A ring, MMAs half by half (see GemmParams::two_pass): needs
+      // a_stages == num_kb; streamed weights (even ring depth is not required: one issuer warp), one store box
+      const int b_block = p.n_inst * ROW_BYTES;
+      p.out_bufs = 1;
+      for (int r = 4; r >= 2 && !chosen; --r)
+        for (int bs = std::max(2, std::min(4, 65536 / b_block)); bs >= 2 && !chosen; --bs)
+          if (fits_f(p.num_kb, bs, r)) { p.b_resident = 0; p.two_pass = 1; chosen = true; }
+    }
+    if (chosen) {
+    } else if (p.cout <= 256 || max_split < 2 || (MODE != 1 && !split_s2)) {
       search(1, 1, false, 2);                                    // weights resident when they fit, else streamed
     } else {
       search(2, max_split, true, 1);
@@ -1317,7 +1377,7 @@ int launch_tc_gemm(kws_handle* h, GemmParams& p, cudaStream_t st) {
   }
   const int grid = std::min(p.num_tiles, h->num_sms / p.n_split) * p.n_split;
   if (grid <= 0) return KWS_OK;
-  if (!conv1 && p.ncta % 64) {                                   // 32-column tail boxes of this launch's output
+  if (!conv1 && (p.two_pass ? p.n_inst : p.ncta) % 64) {         // 32-column tail boxes of this launch's output
     const int rc = make_tensor_map(h, &p.tmap_tail, p.out_act, p.cout, p.out_rows, 1, 32, false, 32);
     if (rc) return rc;
   }
