@@ -22,7 +22,8 @@
 //                            UMMA-swizzled A slab; one mbarrier arrival per warp
 // Pipelines: raw ring (TMA <-> producers), A ring (producers <-> MMA), B ring (loader <-> MMA),
 // accumulator stages in TMEM (MMA <-> epilogue), all on mbarriers; tcgen05.commit releases smem
-// slots / publishes accumulators.
+// slots / publishes accumulators.  Layers with more than 256 columns run with one accumulator stage,
+// or -- when every K slab of a tile fits the A ring -- with two-pass accumulation (GemmParams::two_pass).
 // Operands are fp16 (same tensor rate as bf16, 3 more mantissa bits; ReLU6 bounds activations to
 // [0,6] so the range is safe), accumulation is fp32 in TMEM.  The BatchNorm scale is folded into
 // the fp16 weights at load time, the shift stays fp32 in the epilogue.
@@ -551,10 +552,10 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
   } else if (warp == MMA_WARP) {
     // =========================== MMA issuer ===========================
     // all 32 lanes walk the loop (uniform control flow and registers); one elected lane issues.
-    // A operand ring: conv1 = the A ring (one stage = both slabs of a tile); dw_pw = the raw ring itself
-    // (the producers rewrite each stage in place), freed by this warp's commit.
+    // A operand ring: conv1: one stage = both slabs of a tile; dw_pw: one stage = one K slab; freed by this warp's commit.
     // This warp is the one strictly serial role of the pipeline (every K slab of every tile passes through
-    // it), so its loop keeps every parameter in a register ((() + zi)) and does nothing but wait / fence / issue.
+    // it), so its loop keeps every parameter in a register (the `+ zi` idiom of tc_common.cuh) and does nothing
+    // but wait / fence / issue.
     {
       const uint32_t idesc = ((umma_idesc_f16(TILE_M, p.n_inst, /*fp16*/ 0)) + zi);
       const uint32_t a_lo0 = ((umma_desc_lo(smem_u32(a_base))) + zi), b_lo0 = ((umma_desc_lo(smem_u32(b_base))) + zi);
