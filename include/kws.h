@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define KWS_ABI_VERSION 1
+#define KWS_ABI_VERSION 2
 
 #define KWS_OK            0
 #define KWS_EINVAL       -1   /* bad argument                                   */
@@ -48,8 +48,9 @@ extern "C" {
 
 /* arithmetic of the dense contractions */
 #define KWS_PREC_FP32   0     /* fp32 CUDA-core GEMMs: 1e-4 parity tier          */
-#define KWS_PREC_TC     1     /* tcgen05 tensor-core GEMMs (bf16 / split-fp16 operands,
-                                 fp32 accumulate in TMEM): 1e-2 parity tier       */
+#define KWS_PREC_TC     1     /* tcgen05 tensor-core GEMMs, fp32 accumulate in TMEM: network with fp16
+                                 operands / fp16 activations (1e-2 parity tier), depthwise FIR accumulated in
+                                 fp32; STFT with split-fp16 operands (keeps the fp32 tier's 1e-4)           */
 
 #define KWS_ARCH_195 195      /* model.py:775-838 (also exp 206)                  */
 #define KWS_ARCH_106 106      /* 32-class variant from the logs_106 graph         */
@@ -155,10 +156,26 @@ int kws_vote(kws_t* h, const int32_t* labels, int M, int B, int min_count,
              int32_t* voted, uint8_t* clear, void* stream);
 
 /* ---- host-buffer entry points: what the reference-side binding calls ---- */
+/* All of them run a chunked three-stream pipeline (H2D of chunk k+1 and D2H of chunk k-1 under the kernels of
+ * chunk k) on the handle's own streams and return when the results are in the host buffers.  Host buffers may be
+ * pinned (cudaHostAlloc / cudaHostRegister: copied by DMA straight from / to the caller's memory) or pageable (a
+ * plain np.ndarray / malloc): pageable buffers are staged through pinned slots owned by the handle by a few host
+ * threads (KWS_STAGE_THREADS, default 4), so the overlap holds for them too.  KWS_STAGING_AUTO detects which per
+ * call (cudaPointerGetAttributes); the other two modes force the choice (A/B measurements). */
+#define KWS_STAGING_AUTO   0
+#define KWS_STAGING_ALWAYS 1
+#define KWS_STAGING_NEVER  2
+int kws_set_host_staging(kws_t* h, int mode);
 /* Model.predict(x) + TTA (make_submission.py:120-146): wav_h [B,16000] host fp32 in,
- * probs_h [B,C] / argmax_h [B] host out.  Pinned staging + H2D/D2H copies are inside. */
+ * probs_h [B,C] / argmax_h [B] host out. */
 int kws_predict_host(kws_t* h, int slot, const float* wav_h, int B, const int32_t* view_shift_h,
                      const float* view_gain_h, int n_views, float* probs_h, int32_t* argmax_h);
+/* Same with the clips in the wire format of the reference's WAV files: 16-bit PCM [B,16000], decoded on the device
+ * as float(pcm) / divisor (32768: DecodeWav, input_data.py:334-336; 32767: the scipy paths,
+ * make_submission_on_rpi.py:97, create_pseudo_with_thresh.py:48).  Half the host->device bytes of the fp32 form. */
+int kws_predict_host_pcm16(kws_t* h, int slot, const int16_t* pcm_h, float divisor, int B,
+                           const int32_t* view_shift_h, const float* view_gain_h, int n_views,
+                           float* probs_h, int32_t* argmax_h);
 /* AudioProcessor.get_data body (input_data.py:457-536) for pre-drawn parameters: host
  * waveforms + parameter arrays in, host representation out.  kind = -1 -> 'raw'. */
 int kws_get_data_host(kws_t* h, const float* wav_h, const int32_t* shift_h, const int32_t* bg_file_h,
@@ -171,6 +188,14 @@ int kws_pipeline_host(kws_t* h, int slot, const float* wav_h, const int32_t* shi
                       const float* fg_vol_h, int B, int feat_kind, const int32_t* view_shift_h,
                       const float* view_gain_h, int n_views, float* feat_h, float* probs_h,
                       int32_t* argmax_h);
+
+/* kws_pipeline_host with 16-bit PCM clips (see kws_predict_host_pcm16); the decode is fused into the augment
+ * kernel's load (input_data.py:334-341).  Parameter arrays all NULL = decode only. */
+int kws_pipeline_host_pcm16(kws_t* h, int slot, const int16_t* pcm_h, float divisor, const int32_t* shift_h,
+                            const int32_t* bg_file_h, const int32_t* bg_off_h, const float* bg_vol_h,
+                            const float* fg_vol_h, int B, int feat_kind, const int32_t* view_shift_h,
+                            const float* view_gain_h, int n_views, float* feat_h, float* probs_h,
+                            int32_t* argmax_h);
 
 #ifdef __cplusplus
 }

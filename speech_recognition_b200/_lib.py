@@ -50,6 +50,10 @@ SIGNATURES = {
     "kws_vote": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "kws_predict_host": (_i, [_vp, _i, _vp, _i, C.POINTER(C.c_int32), C.POINTER(_f), _i, _vp, _vp]),
     "kws_get_data_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "kws_set_host_staging": (_i, [_vp, _i]),
+    "kws_predict_host_pcm16": (_i, [_vp, _i, _vp, _f, _i, C.POINTER(C.c_int32), C.POINTER(_f), _i, _vp, _vp]),
+    "kws_pipeline_host_pcm16": (_i, [_vp, _i, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, C.POINTER(C.c_int32),
+                                     C.POINTER(_f), _i, _vp, _vp, _vp]),
     "kws_pipeline_host": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, C.POINTER(C.c_int32),
                                C.POINTER(_f), _i, _vp, _vp, _vp]),
 }

@@ -137,5 +137,10 @@ class AudioProcessor:
             return out.astype(np.float64)       # the reference fills np.zeros((n, dim)) == float64
         rep = self.output_representation
         if rep == 'mfcc_and_raw':
-            return [run('mfcc'), run('raw')], onehot
+            # one augmentation run feeds both outputs, as sess.run([mfcc_, background_clamp_]) does (input_data.py:520-531)
+            raw = run('raw')
+            if n == 0:
+                return [run('mfcc'), raw], onehot
+            mfcc = self.engine.features_host(raw.astype(np.float32), kind='mfcc').astype(np.float64)
+            return [mfcc, raw], onehot
         return run(rep), onehot

@@ -13,10 +13,11 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libkws.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--use_fast_math=false"]
-NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+              "-Xcompiler", "-fPIC"]
 if os.environ.get("KWS_PROFILE_BUILD", "0") not in ("", "0"):       # knockout switches + event trace in the block kernel
     NVCC_FLAGS.append("-DKWS_PROFILE_BUILD=1")
+if os.environ.get("KWS_FIR_FP16", "0") not in ("", "0"):            # A/B aid: the r01 packed-half depthwise FIR
+    NVCC_FLAGS.append("-DKWS_FIR_FP16=1")
 
 
 def _nvcc():

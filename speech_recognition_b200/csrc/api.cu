@@ -1,6 +1,5 @@
-// C ABI of libkws.so (include/kws.h): argument validation, handle lifetime, the
-// host-buffer entry points (pinned-agnostic H2D/D2H pipeline on two streams) and
-// dispatch to the kernel launchers.  No CPU fallback exists anywhere below.
+// C ABI of libkws.so (include/kws.h): argument validation, handle lifetime and dispatch to the kernel
+// launchers (the host-buffer entry points live in host_pipeline.cu).  No CPU fallback exists anywhere below.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -48,7 +47,7 @@ void timer_begin(kws_handle* h, int cls, cudaStream_t st) {
 }
 void timer_end(kws_handle* h, cudaStream_t st) { cudaEventRecord(h->timed.back().e1, st); }
 
-static int make_views(kws_handle* h, const int32_t* shift_h, const float* gain_h, int n, ViewTable* vt) {
+int make_views(kws_handle* h, const int32_t* shift_h, const float* gain_h, int n, ViewTable* vt) {
   if (n <= 0 || n > KWS_MAX_VIEWS) return fail(h, KWS_EINVAL, "n_views must be in 1..16");
   vt->n = n;
   for (int i = 0; i < KWS_MAX_VIEWS; ++i) { vt->shift[i] = 0; vt->gain[i] = 1.0f; }
@@ -59,7 +58,7 @@ static int make_views(kws_handle* h, const int32_t* shift_h, const float* gain_h
   return KWS_OK;
 }
 
-static int forward_dispatch(kws_handle* h, int slot, const float* wav, int B, const ViewTable& vt,
+int forward_dispatch(kws_handle* h, int slot, const float* wav, int B, const ViewTable& vt,
                             float* probs, int32_t* argmax, cudaStream_t st) {
   if (slot < 0 || slot >= KWS_MAX_MODELS || !h->models[slot].loaded)
     return fail(h, KWS_ESTATE, "kws_forward before kws_model_load for this slot");
@@ -70,7 +69,7 @@ static int forward_dispatch(kws_handle* h, int slot, const float* wav, int B, co
                                        : launch_forward_tc(h, h->models[slot], wav, B, vt, probs, argmax, st);
 }
 
-static int features_dispatch(kws_handle* h, const float* wav, int B, int kind, float* out, cudaStream_t st) {
+int features_dispatch(kws_handle* h, const float* wav, int B, int kind, float* out, cudaStream_t st) {
   if (!h->fe.configured) return fail(h, KWS_ESTATE, "kws_features before kws_frontend_config");
   if (kind < KWS_FEAT_SPEC || kind > KWS_FEAT_MFCC) return fail(h, KWS_EINVAL, "unknown feature kind");
   if (B < 0) return fail(h, KWS_EINVAL, "negative batch");
@@ -80,7 +79,13 @@ static int features_dispatch(kws_handle* h, const float* wav, int B, int kind, f
                                        : launch_features_tc(h, wav, B, kind, out, st);
 }
 
-static size_t feat_dim(const kws_handle* h, int kind) {
+int mark_user_stream(kws_handle* h, cudaStream_t st) {
+  if (!h->ev_user) KWS_CUDA(h, cudaEventCreateWithFlags(&h->ev_user, cudaEventDisableTiming));
+  KWS_CUDA(h, cudaEventRecord(h->ev_user, st));
+  return KWS_OK;
+}
+
+size_t feat_dim(const kws_handle* h, int kind) {
   const Frontend& fe = h->fe;
   const int d = kind == KWS_FEAT_SPEC ? fe.n_bins : (kind == KWS_FEAT_LOGMEL ? fe.n_mel : fe.n_keep);
   return static_cast<size_t>(fe.frames) * d;
@@ -137,8 +142,13 @@ void kws_destroy(kws_t* h) {
   for (int i = 0; i < 2; ++i) if (h->act[i]) cudaFree(h->act[i]);
   if (h->spec_ws) cudaFree(h->spec_ws);
   if (h->mel_ws) cudaFree(h->mel_ws);
-  if (h->pinned) cudaFreeHost(h->pinned);
   if (h->stage_d) cudaFree(h->stage_d);
+  for (int i = 0; i < 2; ++i) {
+    if (h->pin_in[i]) cudaFreeHost(h->pin_in[i]);
+    if (h->pin_out[i]) cudaFreeHost(h->pin_out[i]);
+  }
+  if (h->copy_pool) copy_pool_destroy(h->copy_pool);
+  if (h->ev_user) cudaEventDestroy(h->ev_user);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
   if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
@@ -254,7 +264,8 @@ int kws_frontend_frames(const kws_t* h) { return (h && h->fe.configured) ? h->fe
 
 int kws_features(kws_t* h, const float* wav, int B, int kind, float* out, void* stream) {
   if (!h) return KWS_EINVAL;
-  return features_dispatch(h, wav, B, kind, out, static_cast<cudaStream_t>(stream));
+  const int rc = features_dispatch(h, wav, B, kind, out, static_cast<cudaStream_t>(stream));
+  return rc ? rc : (B > 0 ? mark_user_stream(h, static_cast<cudaStream_t>(stream)) : KWS_OK);
 }
 
 int kws_model_load(kws_t* h, int slot, int arch, const kws_tensor_h* tensors_h, int n) {
@@ -275,7 +286,8 @@ int kws_forward(kws_t* h, int slot, const float* wav, int B, const int32_t* view
   ViewTable vt;
   int rc = make_views(h, view_shift_h, view_gain_h, n_views, &vt);
   if (rc) return rc;
-  return forward_dispatch(h, slot, wav, B, vt, probs_mean, argmax, static_cast<cudaStream_t>(stream));
+  rc = forward_dispatch(h, slot, wav, B, vt, probs_mean, argmax, static_cast<cudaStream_t>(stream));
+  return rc ? rc : (B > 0 ? mark_user_stream(h, static_cast<cudaStream_t>(stream)) : KWS_OK);
 }
 
 int kws_debug_activation(kws_t* h, int slot, const float* wav, int B, const int32_t* view_shift_h,
@@ -288,9 +300,10 @@ int kws_debug_activation(kws_t* h, int slot, const float* wav, int B, const int3
   if (layer < 0 || layer > NUM_BLOCKS || !out || !wav || B <= 0) return fail(h, KWS_EINVAL, "bad arguments");
   if (B * n_views > h->max_rows) return fail(h, KWS_EINVAL, "debug activation needs B*n_views <= max_rows");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return h->precision == KWS_PREC_FP32
-             ? launch_forward_f32(h, h->models[slot], wav, B, vt, nullptr, nullptr, st, layer, out)
-             : launch_forward_tc(h, h->models[slot], wav, B, vt, nullptr, nullptr, st, layer, out);
+  rc = h->precision == KWS_PREC_FP32
+           ? launch_forward_f32(h, h->models[slot], wav, B, vt, nullptr, nullptr, st, layer, out)
+           : launch_forward_tc(h, h->models[slot], wav, B, vt, nullptr, nullptr, st, layer, out);
+  return rc ? rc : mark_user_stream(h, st);
 }
 
 int kws_convert_classes(kws_t* h, const float* probs, int B, int C_in, const int32_t* class_map_h,
@@ -312,170 +325,6 @@ int kws_vote(kws_t* h, const int32_t* labels, int M, int B, int min_count, int32
   if (!h) return KWS_EINVAL;
   if (B < 0 || (B > 0 && !labels)) return fail(h, KWS_EINVAL, "bad arguments");
   return launch_vote(h, labels, M, B, min_count, voted, clear, static_cast<cudaStream_t>(stream));
-}
-
-// ------------------------------------------------------------------------------------------
-// Host-buffer entry points.  One staging allocation on the device holds two slots of
-// waveforms, parameters and results; H2D copies, kernels and D2H copies of consecutive chunks
-// run on three streams ordered by per-slot events, so the copies hide under the kernels.
-// Pinned caller buffers make the copies truly asynchronous; pageable ones still work.
-// ------------------------------------------------------------------------------------------
-struct StageLayout {
-  size_t wav, aug, shift, bgf, bgo, bgv, fgv, feat, probs, amax, total;
-};
-
-static StageLayout stage_layout(const kws_handle* h, int nb, int classes, size_t fdim) {
-  StageLayout s{};
-  size_t o = 0;
-  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
-  s.wav = take(static_cast<size_t>(nb) * L * 4);
-  s.aug = take(static_cast<size_t>(nb) * L * 4);
-  s.shift = take(nb * 4); s.bgf = take(nb * 4); s.bgo = take(nb * 4); s.bgv = take(nb * 4); s.fgv = take(nb * 4);
-  s.feat = take(static_cast<size_t>(nb) * fdim * 4);
-  s.probs = take(static_cast<size_t>(nb) * classes * 4);
-  s.amax = take(nb * 4);
-  s.total = o;
-  (void)h;
-  return s;
-}
-
-int kws_pipeline_host(kws_t* h, int slot, const float* wav_h, const int32_t* shift_h,
-                      const int32_t* bg_file_h, const int32_t* bg_off_h, const float* bg_vol_h,
-                      const float* fg_vol_h, int B, int feat_kind, const int32_t* view_shift_h,
-                      const float* view_gain_h, int n_views, float* feat_h, float* probs_h,
-                      int32_t* argmax_h) {
-  if (!h) return KWS_EINVAL;
-  if (B < 0) return fail(h, KWS_EINVAL, "negative batch");
-  if (B == 0) return KWS_OK;
-  if (!wav_h) return fail(h, KWS_EINVAL, "null waveform pointer");
-  KWS_CUDA(h, cudaSetDevice(h->device));
-  const bool do_aug = shift_h || bg_file_h || bg_off_h || bg_vol_h || fg_vol_h;
-  if (do_aug && !(shift_h && bg_file_h && bg_off_h && bg_vol_h && fg_vol_h))
-    return fail(h, KWS_EINVAL, "augmentation parameters must be all present or all NULL");
-  const bool do_feat = feat_kind >= 0;
-  const bool do_fwd = n_views > 0;
-  if (do_feat && !h->fe.configured) return fail(h, KWS_ESTATE, "front end not configured");
-  ViewTable vt{};
-  int classes = 0;
-  if (do_fwd) {
-    int rc = make_views(h, view_shift_h, view_gain_h, n_views, &vt);
-    if (rc) return rc;
-    if (slot < 0 || slot >= KWS_MAX_MODELS || !h->models[slot].loaded) return fail(h, KWS_ESTATE, "model not loaded");
-    classes = h->models[slot].classes;
-  }
-  const size_t fdim = do_feat ? feat_dim(h, feat_kind) : 0;
-  // Chunks of one forward pass worth of clip-views (max_rows), so that with two staging slots
-  // the H2D copy of chunk k+1 (copy stream) and the D2H copy of chunk k-1 (second copy stream)
-  // run under the kernels of chunk k (compute stream); events order the three streams per slot.
-  const int chunk = std::max(1, std::min(std::min(B, 4096), do_fwd ? std::max(1, h->max_rows / n_views) : 2048));
-  const StageLayout lay = stage_layout(h, chunk, std::max(classes, 1), fdim);
-  int rc = ensure_bytes(h, &h->stage_d, &h->stage_bytes, 2 * lay.total);
-  if (rc) return rc;
-  if (!h->h2d_stream) {
-    KWS_CUDA(h, cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
-    KWS_CUDA(h, cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      KWS_CUDA(h, cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
-      KWS_CUDA(h, cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
-      KWS_CUDA(h, cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming));
-    }
-  }
-  cudaStream_t st = h->own_stream, s_in = h->h2d_stream, s_out = h->d2h_stream;
-  int k = 0;
-  // Chunk schedule: the first H2D copy and the last D2H copy are the only ones that cannot hide under kernels,
-  // so the call starts with a short chunk, doubles it (a chunk's H2D copy is ~1.8x faster than the kernels of the
-  // chunk before it, so it stays almost hidden) up to the forward's chunk size -- large chunks run the network
-  // ~8 % faster than small ones -- and ends with a short tail.  (Measured on schedules 1/4..1/16, x1.5..x2.5:
-  // all within 380-400k clips/s at 4096 clips per call; this one was the best.)
-  const int first = std::max(std::min(chunk, 64), std::min(chunk / 16, B / 8));
-  const int tail = std::max(std::min(chunk, 64), std::min(std::min(chunk / 4, 512), B / 8));
-  const bool ramp = B > 2 * first + tail;
-  int next = ramp ? first : chunk;
-  for (int b0 = 0, nb = 0; b0 < B; b0 += nb, ++k) {
-    const int rem = B - b0;
-    nb = std::min(next, rem);
-    if (ramp && rem > tail && rem <= next + tail) nb = rem - tail;          // leave a short tail
-    next = std::min(chunk, 2 * next);
-    const int slot_k = k & 1;
-    char* base = static_cast<char*>(h->stage_d) + slot_k * lay.total;
-    float* d_wav = reinterpret_cast<float*>(base + lay.wav);
-    float* d_aug = reinterpret_cast<float*>(base + lay.aug);
-    // ---- copy stream: inputs of chunk k (its slot was last read by the kernels of chunk k-2) ----
-    if (k >= 2) KWS_CUDA(h, cudaStreamWaitEvent(s_in, h->ev_comp[slot_k], 0));
-    KWS_CUDA(h, cudaMemcpyAsync(d_wav, wav_h + static_cast<size_t>(b0) * L, static_cast<size_t>(nb) * L * 4,
-                                cudaMemcpyHostToDevice, s_in));
-    int32_t* d_shift = reinterpret_cast<int32_t*>(base + lay.shift);
-    int32_t* d_bgf = reinterpret_cast<int32_t*>(base + lay.bgf);
-    int32_t* d_bgo = reinterpret_cast<int32_t*>(base + lay.bgo);
-    float* d_bgv = reinterpret_cast<float*>(base + lay.bgv);
-    float* d_fgv = reinterpret_cast<float*>(base + lay.fgv);
-    if (do_aug) {
-      KWS_CUDA(h, cudaMemcpyAsync(d_shift, shift_h + b0, nb * 4, cudaMemcpyHostToDevice, s_in));
-      KWS_CUDA(h, cudaMemcpyAsync(d_bgf, bg_file_h + b0, nb * 4, cudaMemcpyHostToDevice, s_in));
-      KWS_CUDA(h, cudaMemcpyAsync(d_bgo, bg_off_h + b0, nb * 4, cudaMemcpyHostToDevice, s_in));
-      KWS_CUDA(h, cudaMemcpyAsync(d_bgv, bg_vol_h + b0, nb * 4, cudaMemcpyHostToDevice, s_in));
-      KWS_CUDA(h, cudaMemcpyAsync(d_fgv, fg_vol_h + b0, nb * 4, cudaMemcpyHostToDevice, s_in));
-    }
-    KWS_CUDA(h, cudaEventRecord(h->ev_h2d[slot_k], s_in));
-    // ---- compute stream: kernels of chunk k (its result buffers were last read by D2H of chunk k-2) ----
-    KWS_CUDA(h, cudaStreamWaitEvent(st, h->ev_h2d[slot_k], 0));
-    if (k >= 2) KWS_CUDA(h, cudaStreamWaitEvent(st, h->ev_d2h[slot_k], 0));
-    const float* x = d_wav;
-    if (do_aug) {
-      rc = launch_augment(h, d_wav, nullptr, 1.0f, d_shift, d_bgf, d_bgo, d_bgv, d_fgv, d_aug, nb, 0, st);
-      if (rc) return rc;
-      x = d_aug;
-    }
-    float* d_feat = reinterpret_cast<float*>(base + lay.feat);
-    float* d_probs = reinterpret_cast<float*>(base + lay.probs);
-    int32_t* d_amax = reinterpret_cast<int32_t*>(base + lay.amax);
-    if (do_feat) {
-      rc = features_dispatch(h, x, nb, feat_kind, d_feat, st);
-      if (rc) return rc;
-    }
-    if (do_fwd) {
-      rc = forward_dispatch(h, slot, x, nb, vt, d_probs, d_amax, st);
-      if (rc) return rc;
-    }
-    KWS_CUDA(h, cudaEventRecord(h->ev_comp[slot_k], st));
-    // ---- second copy stream: results of chunk k ----
-    KWS_CUDA(h, cudaStreamWaitEvent(s_out, h->ev_comp[slot_k], 0));
-    if (do_feat) {
-      if (feat_h)
-        KWS_CUDA(h, cudaMemcpyAsync(feat_h + static_cast<size_t>(b0) * fdim, d_feat, static_cast<size_t>(nb) * fdim * 4,
-                                    cudaMemcpyDeviceToHost, s_out));
-    } else if (feat_h && !do_fwd) {                      // 'raw' representation: the augmented waveform
-      KWS_CUDA(h, cudaMemcpyAsync(feat_h + static_cast<size_t>(b0) * L, x, static_cast<size_t>(nb) * L * 4,
-                                  cudaMemcpyDeviceToHost, s_out));
-    }
-    if (do_fwd) {
-      if (probs_h)
-        KWS_CUDA(h, cudaMemcpyAsync(probs_h + static_cast<size_t>(b0) * classes, d_probs,
-                                    static_cast<size_t>(nb) * classes * 4, cudaMemcpyDeviceToHost, s_out));
-      if (argmax_h)
-        KWS_CUDA(h, cudaMemcpyAsync(argmax_h + b0, d_amax, nb * 4, cudaMemcpyDeviceToHost, s_out));
-    }
-    KWS_CUDA(h, cudaEventRecord(h->ev_d2h[slot_k], s_out));
-  }
-  KWS_CUDA(h, cudaStreamSynchronize(s_out));
-  KWS_CUDA(h, cudaStreamSynchronize(st));
-  return KWS_OK;
-}
-
-int kws_predict_host(kws_t* h, int slot, const float* wav_h, int B, const int32_t* view_shift_h,
-                     const float* view_gain_h, int n_views, float* probs_h, int32_t* argmax_h) {
-  if (h && n_views <= 0) return fail(h, KWS_EINVAL, "n_views must be positive");
-  return kws_pipeline_host(h, slot, wav_h, nullptr, nullptr, nullptr, nullptr, nullptr, B, -1, view_shift_h,
-                           view_gain_h, n_views, nullptr, probs_h, argmax_h);
-}
-
-int kws_get_data_host(kws_t* h, const float* wav_h, const int32_t* shift_h, const int32_t* bg_file_h,
-                      const int32_t* bg_off_h, const float* bg_vol_h, const float* fg_vol_h, int B,
-                      int clamp, int kind, float* out_h) {
-  if (h && clamp) return fail(h, KWS_EUNSUPPORTED, "clamp is only available through kws_augment");
-  if (h && !out_h) return fail(h, KWS_EINVAL, "null output pointer");
-  return kws_pipeline_host(h, 0, wav_h, shift_h, bg_file_h, bg_off_h, bg_vol_h, fg_vol_h, B, kind, nullptr,
-                           nullptr, 0, out_h, nullptr, nullptr);
 }
 
 }  // extern "C"

@@ -77,7 +77,7 @@ augment_mix_kernel(const TIn* __restrict__ wav, float pcm_scale,
   const int tid = threadIdx.x;
 
   // ---- rolled waveform window: source index of output t is (t - shift) mod L ----
-  int sm = shift[b] % L;
+  int sm = (shift != nullptr ? shift[b] : 0) % L;      // all five parameter arrays NULL = identity (PCM decode only)
   if (sm < 0) sm += L;
   int j0 = t0 - sm;
   if (j0 < 0) j0 += L;
@@ -92,7 +92,7 @@ augment_mix_kernel(const TIn* __restrict__ wav, float pcm_scale,
   }
 
   // ---- noise-bank window ----
-  const int bf = bg_file[b];
+  const int bf = bg_file != nullptr ? bg_file[b] : -1;
   const bool has_bg = (bf >= 0) && (bf < n_files) && (bank != nullptr);
   int bhead = 0;
   if (has_bg) {
@@ -116,8 +116,8 @@ augment_mix_kernel(const TIn* __restrict__ wav, float pcm_scale,
   cp_async_wait_all();
   __syncthreads();
 
-  const float fv = fg_vol[b];
-  const float bv = bg_vol[b];
+  const float fv = fg_vol != nullptr ? fg_vol[b] : 1.0f;
+  const float bv = bg_vol != nullptr ? bg_vol[b] : 0.0f;
   const int wq = head >> 2, wr = head & 3;
   const int br = bhead;                                 // 0..3
   const QuadT* sq = reinterpret_cast<const QuadT*>(s_wav);

@@ -72,6 +72,8 @@ struct Frontend {
 
 }  // namespace kws
 
+namespace kws { class CopyPool; void copy_pool_destroy(CopyPool*); }
+
 struct kws_handle {
   int device = 0;
   int max_rows = 0;
@@ -95,9 +97,13 @@ struct kws_handle {
   size_t spec_ws_bytes = 0;
   float* mel_ws = nullptr;
   size_t mel_ws_bytes = 0;
-  // host-entry staging
-  void* pinned = nullptr;  size_t pinned_bytes = 0;
+  // host-entry staging (host_pipeline.cu): device slots, and pinned host slots for pageable caller buffers
   void* stage_d = nullptr; size_t stage_bytes = 0;
+  void* pin_in[2] = {nullptr, nullptr};  size_t pin_in_bytes[2] = {0, 0};
+  void* pin_out[2] = {nullptr, nullptr}; size_t pin_out_bytes[2] = {0, 0};
+  kws::CopyPool* copy_pool = nullptr;     // worker threads of the pageable -> pinned staging copies
+  int staging_mode = 0;                   // KWS_STAGING_*
+  cudaEvent_t ev_user = nullptr;          // last use of the handle's workspace on a caller stream (device entry points)
   cudaStream_t own_stream = nullptr;      // compute stream of the host entry points
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
@@ -139,6 +145,17 @@ void timer_begin(kws_handle* h, int cls, cudaStream_t st);
 void timer_end(kws_handle* h, cudaStream_t st);
 #define KWS_T0(h, cls, st) do { if ((h)->timing) kws::timer_begin((h), (cls), (st)); } while (0)
 #define KWS_T1(h, st) do { if ((h)->timing) kws::timer_end((h), (st)); } while (0)
+
+// Device entry points that touch the handle's workspace (activations, front-end intermediates) record this event on
+// the caller's stream; the host entry points, which run on the handle's own streams, wait for it first.
+int mark_user_stream(kws_handle* h, cudaStream_t st);
+
+// ---- dispatch helpers of api.cu used by host_pipeline.cu ----
+int make_views(kws_handle* h, const int32_t* shift_h, const float* gain_h, int n, ViewTable* vt);
+int forward_dispatch(kws_handle* h, int slot, const float* wav, int B, const ViewTable& vt, float* probs,
+                     int32_t* argmax, cudaStream_t st);
+int features_dispatch(kws_handle* h, const float* wav, int B, int kind, float* out, cudaStream_t st);
+size_t feat_dim(const kws_handle* h, int kind);
 
 // ---- launchers implemented in the .cu files ----
 int launch_augment(kws_handle* h, const float* wav, const int16_t* pcm, float pcm_scale,

@@ -194,9 +194,27 @@ __device__ __forceinline__ uint32_t row_meta(const GemmParams& p, int stride, in
 
 __device__ __forceinline__ uint4 lds128(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
 
+// Depthwise k = 3 FIR of one 16-byte chunk (8 channels): fp16 inputs and taps, fp32 accumulation (the mixed-precision
+// FMA of sm_100: fma.rn.f32.f16 = FHFMA, operands taken straight from the packed halves), ONE rounding to the fp16 A
+// operand of the pointwise GEMM.  (Until r02 this was a packed-half chain hmul2 / hfma2 / hfma2 = three fp16
+// roundings; KWS_FIR_FP16=1 at build time restores it for A/B timing.)
+__device__ __forceinline__ float fhfma(uint32_t a, uint32_t b, float c, bool hi) {
+  float d;
+  if (hi) asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\tfma.rn.f32.f16 %0, ah, bh, %3;\n\t}"
+              : "=f"(d) : "r"(a), "r"(b), "f"(c));
+  else asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\tfma.rn.f32.f16 %0, al, bl, %3;\n\t}"
+           : "=f"(d) : "r"(a), "r"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 __device__ __forceinline__ uint4 fir3(const uint4& x0, const uint4& x1, const uint4& x2, const uint4& k0,
                                       const uint4& k1, const uint4& k2) {
   uint4 o;
+#ifdef KWS_FIR_FP16
   const __half2* a = reinterpret_cast<const __half2*>(&x0);
   const __half2* b = reinterpret_cast<const __half2*>(&x1);
   const __half2* c = reinterpret_cast<const __half2*>(&x2);
@@ -206,6 +224,21 @@ __device__ __forceinline__ uint4 fir3(const uint4& x0, const uint4& x1, const ui
   __half2* r = reinterpret_cast<__half2*>(&o);
 #pragma unroll
   for (int q = 0; q < 4; ++q) r[q] = __hfma2(c[q], kc[q], __hfma2(b[q], kb[q], __hmul2(a[q], ka[q])));
+#else
+  const uint32_t* a = reinterpret_cast<const uint32_t*>(&x0);
+  const uint32_t* b = reinterpret_cast<const uint32_t*>(&x1);
+  const uint32_t* c = reinterpret_cast<const uint32_t*>(&x2);
+  const uint32_t* ka = reinterpret_cast<const uint32_t*>(&k0);
+  const uint32_t* kb = reinterpret_cast<const uint32_t*>(&k1);
+  const uint32_t* kc = reinterpret_cast<const uint32_t*>(&k2);
+  uint32_t* r = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float lo = fhfma(c[q], kc[q], fhfma(b[q], kb[q], fhfma(a[q], ka[q], 0.0f, false), false), false);
+    const float hi = fhfma(c[q], kc[q], fhfma(b[q], kb[q], fhfma(a[q], ka[q], 0.0f, true), true), true);
+    r[q] = pack_f16x2(lo, hi);
+  }
+#endif
   return o;
 }
 

@@ -26,6 +26,26 @@ def _hp(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
+def _in(a, dtype, shape, name):
+    """Host INPUT array for the C ABI: C-contiguous, exact dtype (converted if needed), checked shape."""
+    a = np.ascontiguousarray(a, dtype)
+    if a.shape != tuple(shape):
+        raise ValueError(f"{name}: expected shape {tuple(shape)}, got {a.shape}")
+    return a
+
+
+def _out(a, dtype, shape, name):
+    """Host OUTPUT array: allocated if None; a caller-supplied one must already be writable, C-contiguous, of the
+    exact dtype and hold exactly prod(shape) elements (the D2H copy would otherwise overrun or misinterpret it)."""
+    if a is None:
+        return np.empty(shape, dtype)
+    if not isinstance(a, np.ndarray) or a.dtype != np.dtype(dtype) or not a.flags.c_contiguous or not a.flags.writeable:
+        raise ValueError(f"{name}: need a writable C-contiguous {np.dtype(dtype).name} ndarray")
+    if a.size != int(np.prod(shape)):
+        raise ValueError(f"{name}: expected {int(np.prod(shape))} elements for shape {tuple(shape)}, got {a.size}")
+    return a
+
+
 class Engine:
     def __init__(self, device: int = 0, max_rows: int = 2048, precision: str | int = "tc"):
         self.lib = _lib.load()
@@ -62,6 +82,22 @@ class Engine:
     @staticmethod
     def _dp(t):
         return C.c_void_p(t.data_ptr()) if t is not None else None
+
+    def _dev(self, t, dtype, shape, name):
+        """Device tensor handed to the C ABI as a raw pointer: right device, dtype, shape and contiguous."""
+        import torch
+        if not isinstance(t, torch.Tensor) or not t.is_cuda or t.device.index != self.device:
+            raise ValueError(f"{name}: need a torch tensor on cuda:{self.device}")
+        if t.dtype != dtype or not t.is_contiguous():
+            raise ValueError(f"{name}: need a contiguous {dtype} tensor, got {t.dtype} (contiguous={t.is_contiguous()})")
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t
+
+    def set_host_staging(self, mode="auto"):
+        """How the *_host entry points treat caller buffers: 'auto' (pinned -> DMA in place, pageable -> staged
+        through the handle's pinned slots), 'always', 'never' (kws_set_host_staging)."""
+        self._check(self.lib.kws_set_host_staging(self.h, {"auto": 0, "always": 1, "never": 2}[mode]))
 
     def set_precision(self, precision):
         p = {"fp32": PREC_FP32, "tc": PREC_TC}.get(precision, precision)
@@ -104,6 +140,12 @@ class Engine:
         B = wav_t.shape[0]
         if out_t is None:
             out_t = torch.empty((B, SAMPLES), dtype=torch.float32, device=wav_t.device)
+        self._dev(wav_t, wav_t.dtype if wav_t.dtype == torch.int16 else torch.float32, (B, SAMPLES), "wav")
+        self._dev(out_t, torch.float32, (B, SAMPLES), "out")
+        for nm, t, dt in (("time_shift", shift_t, torch.int32), ("bg_index", bg_file_t, torch.int32),
+                          ("bg_offset", bg_off_t, torch.int32), ("bg_volume", bg_vol_t, torch.float32),
+                          ("fg_volume", fg_vol_t, torch.float32)):
+            self._dev(t, dt, (B,), nm)
         if wav_t.dtype == torch.int16:
             self._check(self.lib.kws_augment_pcm16(self.h, self._dp(wav_t), float(pcm_divisor or 32768.0),
                                                    self._dp(shift_t), self._dp(bg_file_t), self._dp(bg_off_t),
@@ -146,6 +188,10 @@ class Engine:
         fr, d = self.feature_shape(k)
         if out_t is None:
             out_t = torch.empty((B, fr, d), dtype=torch.float32, device=wav_t.device)
+        self._dev(wav_t, torch.float32, (B, SAMPLES), "wav")
+        self._dev(out_t, torch.float32, None, "out")
+        if out_t.numel() != B * fr * d:
+            raise ValueError(f"out: expected {B * fr * d} elements, got {out_t.numel()}")
         self._check(self.lib.kws_features(self.h, self._dp(wav_t), B, k, self._dp(out_t), self._stream()))
         return out_t
 
@@ -167,6 +213,7 @@ class Engine:
     def forward(self, wav_t, views=((0, 1.0),), slot=0, want_probs=True, want_argmax=True):
         import torch
         B = wav_t.shape[0]
+        self._dev(wav_t, torch.float32, (B, SAMPLES), "wav")
         Cn = self.classes(slot)
         sh, ga, n = _views(views)
         probs = torch.empty((B, Cn), dtype=torch.float32, device=wav_t.device) if want_probs else None
@@ -179,6 +226,7 @@ class Engine:
         """fp32 activation after `layer` (0 = conv1d_1, i = block i); shape = (T, C) of that layer."""
         import torch
         B = wav_t.shape[0]
+        self._dev(wav_t, torch.float32, (B, SAMPLES), "wav")
         sh, ga, n = _views(views)
         out = torch.empty((B * n, shape[0], shape[1]), dtype=torch.float32, device=wav_t.device)
         self._check(self.lib.kws_debug_activation(self.h, slot, self._dp(wav_t), B, sh, ga, n, int(layer),
@@ -189,6 +237,7 @@ class Engine:
     def convert_classes(self, probs_t, class_map, n_out=12):
         import torch
         B, Cin = probs_t.shape
+        self._dev(probs_t, torch.float32, None, "probs")
         cm = (C.c_int32 * Cin)(*[int(c) for c in class_map])
         out = torch.empty((B, n_out), dtype=torch.float32, device=probs_t.device)
         u8 = torch.empty((B, n_out), dtype=torch.uint8, device=probs_t.device)
@@ -199,6 +248,7 @@ class Engine:
     def select(self, probs_u8_t, thresh: float):
         import torch
         B, Cn = probs_u8_t.shape
+        self._dev(probs_u8_t, torch.uint8, None, "probs_u8")
         label = torch.empty((B,), dtype=torch.int32, device=probs_u8_t.device)
         keep = torch.empty((B,), dtype=torch.uint8, device=probs_u8_t.device)
         self._check(self.lib.kws_select(self.h, self._dp(probs_u8_t), B, Cn, float(thresh), self._dp(label),
@@ -208,6 +258,7 @@ class Engine:
     def vote(self, labels_t, min_count=3):
         import torch
         M, B = labels_t.shape
+        self._dev(labels_t, torch.int32, None, "labels")
         voted = torch.empty((B,), dtype=torch.int32, device=labels_t.device)
         clear = torch.empty((B,), dtype=torch.uint8, device=labels_t.device)
         self._check(self.lib.kws_vote(self.h, self._dp(labels_t), M, B, int(min_count), self._dp(voted),
@@ -215,38 +266,82 @@ class Engine:
         return voted, clear
 
     # -- host-buffer entry points (NumPy in / NumPy out) --
-    def predict_host(self, wav: np.ndarray, views=((0, 1.0),), slot=0, probs_out=None, argmax_out=None):
-        wav = np.ascontiguousarray(wav, np.float32)
+    @staticmethod
+    def _wav_in(wav):
+        """[B,16000] float32, or int16 PCM (the WAV wire format) -- anything else is converted to float32."""
+        wav = np.asarray(wav)
+        dt = np.int16 if wav.dtype == np.int16 else np.float32
+        if wav.ndim != 2 or wav.shape[1] != SAMPLES:
+            raise ValueError(f"wav: expected shape (B, {SAMPLES}), got {wav.shape}")
+        return np.ascontiguousarray(wav, dt)
+
+    def predict_host(self, wav: np.ndarray, views=((0, 1.0),), slot=0, probs_out=None, argmax_out=None,
+                     pcm_divisor=32768.0):
+        wav = self._wav_in(wav)
         B = wav.shape[0]
         Cn = self.classes(slot)
         sh, ga, n = _views(views)
-        probs = probs_out if probs_out is not None else np.empty((B, Cn), np.float32)
-        amax = argmax_out if argmax_out is not None else np.empty((B,), np.int32)
-        self._check(self.lib.kws_predict_host(self.h, slot, _hp(wav), B, sh, ga, n, _hp(probs), _hp(amax)))
+        probs = _out(probs_out, np.float32, (B, Cn), "probs_out")
+        amax = _out(argmax_out, np.int32, (B,), "argmax_out")
+        if wav.dtype == np.int16:
+            self._check(self.lib.kws_predict_host_pcm16(self.h, slot, _hp(wav), float(pcm_divisor), B, sh, ga, n,
+                                                        _hp(probs), _hp(amax)))
+        else:
+            self._check(self.lib.kws_predict_host(self.h, slot, _hp(wav), B, sh, ga, n, _hp(probs), _hp(amax)))
         return probs, amax
 
     def get_data_host(self, wav, shift, bg_file, bg_off, bg_vol, fg_vol, kind="raw", out=None):
         wav = np.ascontiguousarray(wav, np.float32)
+        if wav.ndim != 2 or wav.shape[1] != SAMPLES:
+            raise ValueError(f"wav: expected shape (B, {SAMPLES}), got {wav.shape}")
         B = wav.shape[0]
         k = _KIND.get(kind, kind)
         dim = SAMPLES if k == FEAT_RAW else int(np.prod(self.feature_shape(k)))
-        if out is None:
-            out = np.empty((B, dim), np.float32)
-        args = [np.ascontiguousarray(shift, np.int32), np.ascontiguousarray(bg_file, np.int32),
-                np.ascontiguousarray(bg_off, np.int32), np.ascontiguousarray(bg_vol, np.float32),
-                np.ascontiguousarray(fg_vol, np.float32)]
+        out = _out(out, np.float32, (B, dim), "out")
+        args = [_in(shift, np.int32, (B,), "time_shift"), _in(bg_file, np.int32, (B,), "bg_index"),
+                _in(bg_off, np.int32, (B,), "bg_offset"), _in(bg_vol, np.float32, (B,), "bg_volume"),
+                _in(fg_vol, np.float32, (B,), "fg_volume")]
         self._check(self.lib.kws_get_data_host(self.h, _hp(wav), *[_hp(a) for a in args], B, 0, k, _hp(out)))
         return out
 
+    def features_host(self, wav, kind="mfcc", out=None):
+        """STFT / log-mel / MFCC of host waveforms as they are (no augmentation) -> float32 [B, frames*dim]."""
+        wav = np.ascontiguousarray(wav, np.float32)
+        if wav.ndim != 2 or wav.shape[1] != SAMPLES:
+            raise ValueError(f"wav: expected shape (B, {SAMPLES}), got {wav.shape}")
+        B = wav.shape[0]
+        k = _KIND.get(kind, kind)
+        out = _out(out, np.float32, (B, int(np.prod(self.feature_shape(k)))), "out")
+        self._check(self.lib.kws_get_data_host(self.h, _hp(wav), None, None, None, None, None, B, 0, k, _hp(out)))
+        return out
+
     def pipeline_host(self, wav, params, feat_kind="logmel", views=((0, 1.0),), slot=0,
-                      feat_out=None, probs_out=None, argmax_out=None):
-        """augment -> features -> TTA forward on host buffers (the north-star path)."""
+                      feat_out=None, probs_out=None, argmax_out=None, want_features=True, pcm_divisor=32768.0):
+        """augment -> features -> TTA forward on host buffers (the north-star path).  ``wav`` is float32 or int16
+        PCM [B,16000]; ``params`` holds the five pre-drawn parameter arrays (int64 / float64 inputs, NumPy's
+        defaults, are converted).  ``want_features=False`` still computes the features on the device but leaves
+        them there (the shipped networks consume the raw waveform, make_submission.py:46)."""
+        wav = self._wav_in(wav)
         B = wav.shape[0]
         k = _KIND.get(feat_kind, feat_kind)
         sh, ga, n = _views(views)
         p = params
-        self._check(self.lib.kws_pipeline_host(
-            self.h, slot, _hp(wav), _hp(p["time_shift"]), _hp(p["bg_index"]), _hp(p["bg_offset"]),
-            _hp(p["bg_volume"]), _hp(p["fg_volume"]), B, k, sh, ga, n, _hp(feat_out), _hp(probs_out),
-            _hp(argmax_out)))
-        return feat_out, probs_out, argmax_out
+        pa = [_in(p["time_shift"], np.int32, (B,), "time_shift"), _in(p["bg_index"], np.int32, (B,), "bg_index"),
+              _in(p["bg_offset"], np.int32, (B,), "bg_offset"), _in(p["bg_volume"], np.float32, (B,), "bg_volume"),
+              _in(p["fg_volume"], np.float32, (B,), "fg_volume")]
+        feat = None
+        if want_features or feat_out is not None:
+            dim = SAMPLES if k == FEAT_RAW else int(np.prod(self.feature_shape(k)))
+            feat = _out(feat_out, np.float32, (B, dim), "feat_out")
+        probs = amax = None
+        if n > 0:
+            probs = _out(probs_out, np.float32, (B, self.classes(slot)), "probs_out")
+            amax = _out(argmax_out, np.int32, (B,), "argmax_out")
+        if wav.dtype == np.int16:
+            self._check(self.lib.kws_pipeline_host_pcm16(
+                self.h, slot, _hp(wav), float(pcm_divisor), *[_hp(a) for a in pa], B, k, sh, ga, n, _hp(feat),
+                _hp(probs), _hp(amax)))
+        else:
+            self._check(self.lib.kws_pipeline_host(
+                self.h, slot, _hp(wav), *[_hp(a) for a in pa], B, k, sh, ga, n, _hp(feat), _hp(probs), _hp(amax)))
+        return feat, probs, amax

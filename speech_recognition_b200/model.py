@@ -28,7 +28,8 @@ class Model:
     def predict(self, x, batch_size=32, verbose=0, views=((0, 1.0),)):
         """x: float32 [N,16000] -> float32 [N,C] softmax probabilities.  ``batch_size`` is
         accepted for API compatibility; the device batches internally."""
-        x = np.ascontiguousarray(x, np.float32)
+        x = np.asarray(x)
+        x = np.ascontiguousarray(x, np.int16 if x.dtype == np.int16 else np.float32)   # int16 PCM is decoded on the device
         if x.ndim != 2 or x.shape[1] != 16000:
             raise ValueError("Error when checking input: expected input_1 to have shape (None, 16000) "
                              "but got array with shape %s" % (x.shape,))
@@ -37,9 +38,7 @@ class Model:
 
     def predict_tta(self, x, views=TTA_SHIPPED):
         """(probs + loud_probs + left_probs) / 3 and argmax (make_submission.py:120-146)."""
-        x = np.ascontiguousarray(x, np.float32)
         return self.engine.predict_host(x, views=views, slot=self.slot)
-
 
     def predict_speed_tta(self, x, x_slow):
         """make_submission.py:124-146 with ``use_speed_tta``: x_slow holds the time-stretched copies that

@@ -67,6 +67,51 @@ def make_clips(n: int, seed: int = SEED, return_pcm: bool = False):
     return (clips, out) if return_pcm else clips
 
 
+def make_word_clips(n: int, n_classes: int = 12, seed: int = SEED, device="cpu", return_labels: bool = False):
+    """n synthetic "keyword" clips [n,16000] f32 (torch tensor on `device`), int16-quantised like decoded PCM.
+
+    Class 0 is silence (noise floor only, `_silence_`); class c >= 1 is a fixed three-partial chirp pattern with
+    an amplitude-modulated envelope (a stand-in for one spoken word: the pattern is the word, the per-clip
+    amplitude / onset / pitch jitter / phases / noise floor are the speaker).  Unlike `make_clips` (random mixtures with
+    no class structure) these clips can be CLASSIFIED, which is what the label-agreement tests need: a network
+    TRAINED on them (`trained_weights(arch)`, tools/train_synth_ckpt.py) is confident on its inputs the way the
+    reference's trained checkpoints are on speech.  Written with torch
+    ops so that 100k+ distinct clips can be generated on the GPU in a second (tests); the label of clip i is
+    (seed-dependent) `labels[i]`."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(int(seed))
+    f32 = torch.float32
+    labels = torch.randint(0, n_classes, (n,), generator=g, device=device)
+    # per-class pattern table (host RandomState: identical on every device)
+    rs = np.random.RandomState(1000 + n_classes)
+    f0 = rs.uniform(200.0, 3800.0, (n_classes, 3))
+    slope = rs.uniform(-800.0, 800.0, (n_classes, 3))
+    rel = rs.uniform(0.3, 1.0, (n_classes, 3))
+    dur = rs.uniform(0.25, 0.6, (n_classes,))
+    am = rs.uniform(3.0, 12.0, (n_classes,))
+    tab = lambda a: torch.as_tensor(a, dtype=f32, device=device)[labels]          # noqa: E731
+    f0, slope, rel, dur, am = tab(f0), tab(slope), tab(rel), tab(dur), tab(am)
+    u = lambda lo, hi, shape: lo + (hi - lo) * torch.rand(shape, generator=g, device=device, dtype=f32)   # noqa: E731
+    amp = u(0.08, 0.35, (n, 1))
+    start = u(0.1, 0.35, (n, 1))
+    jitter = 1.0 + 0.01 * torch.randn((n, 1), generator=g, device=device, dtype=f32)
+    phase = u(0.0, 2 * np.pi, (n, 3))
+    t = (torch.arange(SAMPLES, device=device, dtype=f32) / SAMPLES)[None, :]
+    tt = torch.clamp(t - start, min=0.0)
+    env = torch.clamp(tt / 0.02, 0, 1) * torch.clamp((start + dur[:, None] - t) / 0.05, 0, 1)
+    env = env * (0.75 + 0.25 * torch.sin(2 * np.pi * am[:, None] * tt))
+    x = 0.002 * torch.randn((n, SAMPLES), generator=g, device=device, dtype=f32)
+    tone = torch.zeros((n, SAMPLES), device=device, dtype=f32)
+    for j in range(3):
+        ph = 2 * np.pi * jitter * (f0[:, j:j + 1] * tt + 0.5 * slope[:, j:j + 1] * tt * tt) + phase[:, j:j + 1]
+        tone += rel[:, j:j + 1] * torch.sin(ph)
+    x += (labels != 0).to(f32)[:, None] * amp * env * tone / 3.0
+    x -= 0.00064
+    pcm = torch.clamp(torch.round(x * 32768.0), -32768, 32767)
+    clips = (pcm * (1.0 / 32768.0)).to(f32)
+    return (clips, labels) if return_labels else clips
+
+
 def make_noise_bank(seconds: int = 60, seed: int = SEED + 7):
     """6 coloured-noise files -> (bank f32 [sum_len], file_offsets i64 [7])."""
     rs = np.random.RandomState(seed)
@@ -110,6 +155,22 @@ def raw_synthetic_weights(arch: int, seed: int | None = None, head_gain: float |
                 v = v * attn_gain
         w[name] = v.astype(np.float32)
     return w
+
+
+def trained_weights(arch: int):
+    """A TRAINED checkpoint of architecture 195 or 106 keyed by Keras variable name (``data/trained_<arch>.npz``,
+    stored as float16): tools/train_synth_ckpt.py trained the torch restatement of the reference model on the
+    synthetic keyword task of `make_word_clips` (the reference's own checkpoints are not in the mount).
+    Random weights make a chaotic, undecided network (it amplifies input and rounding noise and its softmax sits
+    near ties); this one behaves like the reference's: ~100 % accurate and confident on its data."""
+    path = os.path.join(_DATA, f"trained_{arch}.npz")
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path} missing: run tools/train_synth_ckpt.py")
+    shapes = weight_shapes(arch)
+    with np.load(path) as z:
+        w = {k: z[k].astype(np.float32) for k in z.files}
+    assert set(w) == set(shapes) and all(w[k].shape == tuple(shapes[k]) for k in shapes)
+    return {k: w[k] for k in shapes}
 
 
 def synthetic_weights(arch: int, calibrated: bool = True):

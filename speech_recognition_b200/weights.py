@@ -27,9 +27,9 @@ def validate(arch: int, weights: dict) -> dict:
         if name not in weights:
             raise KeyError(f"missing variable {name!r} for architecture {arch}")
         a = np.ascontiguousarray(weights[name], np.float32)
-        if int(np.prod(a.shape)) != int(np.prod(shp)):
-            raise ValueError(f"{name}: shape {a.shape} does not match {shp}")
-        out[name] = a.reshape(shp)
+        if tuple(a.shape) != tuple(shp):          # same element count in another layout would load silently wrong
+            raise ValueError(f"{name}: shape {a.shape} does not match {tuple(shp)}")
+        out[name] = a
     return out
 
 

@@ -25,7 +25,7 @@ def test_library_exports_header():
     for s in syms:
         assert hasattr(lib, s), f"libkws.so does not export {s}"
         assert s in _lib.SIGNATURES, f"ctypes binding missing for {s}"
-    assert lib.kws_abi_version() == 1
+    assert lib.kws_abi_version() == 2
 
 
 def test_no_cpu_fallback():
