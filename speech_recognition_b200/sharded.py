@@ -85,10 +85,10 @@ class ShardedPredictor:
         if dev is None:
             dev = f"cuda:{self.engine.device}" if self.engine is not None else "cpu"
         p_t = torch.as_tensor(np.ascontiguousarray(probs, np.float32)).to(dev)
-        a_t = torch.as_tensor(np.ascontiguousarray(amax, np.int32)).to(dev)
-        p_all = all_gather_rows(p_t, n, self.group)
-        a_all = all_gather_rows(a_t, n, self.group)
-        return p_all.cpu().numpy(), a_all.cpu().numpy()
+        # ONE collective: the labels are the first-index argmax of the gathered mean probabilities
+        # (make_submission.py:146), which is exactly what the rank-local kernel computed from the same floats
+        p_all = all_gather_rows(p_t, n, self.group).cpu().numpy()
+        return p_all, p_all.argmax(axis=1).astype(np.int32)
 
 
 def sharded_pseudo_labels(engine, probs32_local, n: int, thresh: float, order="heng", group=None):

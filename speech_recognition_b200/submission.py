@@ -44,7 +44,7 @@ def write_submission_csvs(prefix, fnames, probs, pred, wanted_only=False):
         w = csv.writer(f)
         w.writerow(['fname', 'label'] + [int2label[i] for i in range(len(int2label))])
         for fn, l, p in zip(fnames, labels, probs):
-            w.writerow([fn, l] + [repr(float(v)) for v in p])
+            w.writerow([fn, l] + [str(v) for v in np.asarray(p, np.float32)])   # pandas' float32 text: shortest round-trip repr
     return labels, wanted
 
 

@@ -158,7 +158,7 @@ def raw_synthetic_weights(arch: int, seed: int | None = None, head_gain: float |
 
 
 def trained_weights(arch: int):
-    """A TRAINED checkpoint of architecture 195 or 106 keyed by Keras variable name (``data/trained_<arch>.npz``,
+    """A TRAINED checkpoint (195, 106, or 206 = the 195 architecture from another seed) keyed by Keras variable name (``data/trained_<arch>.npz``,
     stored as float16): tools/train_synth_ckpt.py trained the torch restatement of the reference model on the
     synthetic keyword task of `make_word_clips` (the reference's own checkpoints are not in the mount).
     Random weights make a chaotic, undecided network (it amplifies input and rounding noise and its softmax sits

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_json_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1",
-                        "--warmup", "0", "--ref-seconds", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, r.stdout
@@ -22,6 +22,9 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["config"]["workload"].startswith("config3")
+    # the reference arm reports what it really ran: K timed batches of 64 clips, measured ms per step
+    assert d["steps"] == 1 and d["config"]["batch_per_gpu"] == 64
+    assert abs(d["ms_per_step"] * d["value"] / 1e3 - 64) < 1e-6
 
 
 def test_reference_arm_other_ranks_exit_silently():

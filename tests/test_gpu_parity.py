@@ -244,7 +244,10 @@ def test_convert_32_to_12(engine):
         np.testing.assert_allclose(out.cpu().numpy(), r_sm, rtol=2e-6, atol=1e-7)
         d = np.abs(u8.cpu().numpy().astype(int) - r_u8.astype(int))
         assert d.max() <= 1 and (d > 0).mean() < 1e-3          # trunc(p*255) at a 1-ulp knife edge
-        assert np.array_equal(u8.cpu().numpy().argmax(1), r_u8.argmax(1)) or (d > 0).any()
+        top2 = np.sort(r_u8.astype(int), axis=1)
+        clear = (top2[:, -1] - top2[:, -2]) > 1                 # a +-1 knife-edge difference cannot reorder these rows
+        assert clear.mean() > 0.9
+        assert np.array_equal(u8.cpu().numpy().argmax(1)[clear], r_u8.argmax(1)[clear])
 
 
 # --------------------------------------------------------------------------- host entry points
@@ -317,8 +320,9 @@ def test_forward_tc(engine, arch, views):
     r_probs, r_pred = driver.tta_predict(lambda v: network.forward(v, w, arch, dtype=torch.float64), x, views)
     got = probs.cpu().numpy()
     err = np.abs(got - r_probs)
-    # fp16-operand tier: rounding noise of 12 stacked layers reaches the logits at the 1e-2 level
-    # (north_star: 1e-2 on tensor-core GEMMs); probabilities: 99% of entries within 1e-2, none beyond 0.1
+    # fp16-operand tier on the RANDOM-weight nets: a random net amplifies rounding noise from layer to layer (the
+    # trained checkpoints do not: tests/test_gpu_agreement.py holds those to 1e-2 max and 99.9 % labels on 100k clips);
+    # here: 99% of the probabilities within 1e-2, none beyond 0.1, labels equal wherever the top-2 margin exceeds 0.1
     assert np.quantile(err, 0.99) < 1e-2 and err.max() < 0.1, (np.quantile(err, 0.99), err.max())
     margin = np.sort(r_probs, axis=1)
     confident = (margin[:, -1] - margin[:, -2]) > 0.1              # labels may only flip on near-ties

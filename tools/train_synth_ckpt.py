@@ -38,7 +38,7 @@ class Net(nn.Module):
             self.pw.append(nn.Conv1d(c, co, 1, bias=False))
             self.bn.append(nn.BatchNorm1d(co, eps=1e-3, momentum=0.01))
             c = co
-        T = network.layer_lengths(195)[-1]
+        T = network.layer_lengths(arch)[-1]
         self.T, self.C = T, c
         self.d1 = nn.Linear(T * c, T, bias=a["dense1_bias"])
         feat = 2 * c if a["pool"] == "max_avg" else c
@@ -94,6 +94,8 @@ def augment(x, g, bank):
 
 
 def train(arch, steps, batch=64, pool=8192):
+    """arch 206 = the exp-195 architecture trained from another seed on another draw of the clips (the reference's
+    exp 206 is exactly that: the same model retrained, README.md)."""
     torch.manual_seed(arch)
     g = torch.Generator().manual_seed(arch + 1)
     C = network.ARCHS[arch]["classes"]
@@ -137,5 +139,5 @@ def train(arch, steps, batch=64, pool=8192):
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
-    for arch in ([int(sys.argv[1])] if len(sys.argv) > 1 else [195, 106]):
+    for arch in ([int(sys.argv[1])] if len(sys.argv) > 1 else [195, 106, 206]):
         train(arch, steps)
