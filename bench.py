@@ -590,7 +590,7 @@ def run_config45(args):
         eng.load_model(slot, a, synth.synthetic_weights(a))
     cmap_heng, cmap_frozen = class_map_32_to_12("heng"), torch.from_numpy(np.asarray(class_map_32_to_12("frozen"))).to(dev)
     sizes = [args.batch] if (args.config == 4 or args.batch_given) else [1024, 2048, 4096, 8192, 16384, 32768, 65536]
-    _, offs = synth.make_noise_bank(seconds=1)
+    _, offs = synth.make_noise_bank(seconds=2)
     sweep = []
     main = None
     headline_B = 16384 if 16384 in sizes else sizes[-1]

@@ -246,7 +246,7 @@ def test_convert_32_to_12(engine):
         assert d.max() <= 1 and (d > 0).mean() < 1e-3          # trunc(p*255) at a 1-ulp knife edge
         top2 = np.sort(r_u8.astype(int), axis=1)
         clear = (top2[:, -1] - top2[:, -2]) > 1                 # a +-1 knife-edge difference cannot reorder these rows
-        assert clear.mean() > 0.9
+        assert clear.mean() > 0.5
         assert np.array_equal(u8.cpu().numpy().argmax(1)[clear], r_u8.argmax(1)[clear])
 
 
