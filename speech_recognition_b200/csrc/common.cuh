@@ -107,6 +107,10 @@ struct kws_handle {
   cudaStream_t own_stream = nullptr;      // compute stream of the host entry points
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  // cuTensorMapEncodeTiled results keyed by (buffer, shape, box): the activation buffers and chunk sizes repeat from
+  // call to call, so every launch after the first of a shape finds its tensor maps here (tc_net.cu)
+  struct TmapEntry { const void* act; int c; long long d1, d2; int box_rows, swizzle, box_ch; alignas(64) unsigned char map[128]; };
+  std::vector<TmapEntry> tmap_cache;
   // optional per-kernel-class device timing (bench.py roofline): event pairs around launches
   bool timing = false;
   struct TimedLaunch { int cls; cudaEvent_t e0, e1; };

@@ -960,6 +960,30 @@ __device__ __forceinline__ uint4 shfl_down4(const uint4& v, int d) {
                     __shfl_down_sync(0xffffffffu, v.z, d), __shfl_down_sync(0xffffffffu, v.w, d));
 }
 
+// fp16 x fp16 + fp32 -> fp32 with the halves picked from packed registers (FHFMA with .H0 / .H1 operand selectors)
+#define KWS_FHFMA(AH, BH)                                                                                   \
+  asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\t"                     \
+      "fma.rn.f32.f16 %0, " AH ", " BH ", %3;\n\t}"                                                          \
+      : "=f"(d) : "r"(a), "r"(b), "f"(c))
+template <bool A_HI, bool B_HI>
+__device__ __forceinline__ float fhfma_sel(uint32_t a, uint32_t b, float c) {
+  float d;
+  if constexpr (A_HI && B_HI) KWS_FHFMA("ah", "bh");
+  else if constexpr (A_HI) KWS_FHFMA("ah", "bl");
+  else if constexpr (B_HI) KWS_FHFMA("al", "bh");
+  else KWS_FHFMA("al", "bl");
+  return d;
+}
+#undef KWS_FHFMA
+
+// kT (c0 == 128): conv1d_1 is computed TRANSPOSED -- D1^T[channel, time] = W80^T x window^T, i.e. the weight image is
+// the A operand (M = 128 channels) and the staged window rows are the B operand (N = 128 time steps); both are K-major
+// SW128 slabs, so only the two descriptors swap.  A TMEM lane then holds ONE channel over time, and the middle
+// warps (lane = channel) do gain / BN shift / ReLU6 / fp16 rounding and the k = 3 depthwise FIR along the registers of
+// a thread: no shared-memory round trip, no barrier between the middle warps, per-thread scalar shift and taps.  The
+// accumulator of a (clip, view group, tile) unit is read from TMEM ONCE into registers and reused for every member
+// view of the group (TMEM reads are 64 B / cycle / SM; re-reading it per view was a third of the kernel's floor).
+template <bool kT>
 __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __grid_constant__ FusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   const FusedSmem lay = fused_smem(p.c0, p.c1);
@@ -1013,7 +1037,8 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t acc2_col0 = 2u * p.c0;
+  const uint32_t acc1_cols = kT ? static_cast<uint32_t>(TILE_M) : static_cast<uint32_t>(p.c0);   // columns of one conv1d_1 accumulator stage
+  const uint32_t acc2_col0 = 2u * acc1_cols;
 
   // Each CTA works on a contiguous range of units (tile j of view group g of clip b, j fastest): the (b, g, j) of
   // the next unit is an increment (the divisions of decode() were ~700 cycles of the middle warps' chain per unit),
@@ -1030,7 +1055,75 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
     if (++j == p.blocks_per_view) { j = 0; if (++g == p.vg.n_groups) { g = 0; ++b; } }
   };
 
-  if (warp < FUSE_MID_WARPS) {
+  if (kT && warp < FUSE_MID_WARPS) {
+    // =========================== middle (transposed): lane = channel, registers = time ===========================
+    // warp = (lane quarter q, time half hf): channel c = 32 q + lane, block-1 rows [64 hf, 64 hf + 64) of the tile
+    // (rows 126, 127 of the second half are computed from zeros and never stored to global memory).
+    const int q = warp & 3, hf = warp >> 2;
+    const int c = q * 32 + lane;
+    const float shift = s_sh1[c];
+    const uint32_t k01 = static_cast<uint32_t>(__half_as_ushort(s_taps[c])) |
+                         (static_cast<uint32_t>(__half_as_ushort(s_taps[p.c0 + c])) << 16);     // taps 0, 1 of this channel
+    const uint32_t k2 = static_cast<uint32_t>(__half_as_ushort(s_taps[2 * p.c0 + c]));           // tap 2
+    // A2[t][c] in the K-major SW128 slabs of the pointwise GEMM: slab c / 64, row t, 16-byte chunk ((c % 64) / 8) ^ (t % 8)
+    uint32_t off[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      off[r] = smem_u32(a2_base) + static_cast<uint32_t>(c >> 6) * A_SLAB_BYTES + static_cast<uint32_t>(64 * hf + r) * ROW_BYTES +
+               ((((static_cast<uint32_t>(c) & 63u) >> 3) ^ static_cast<uint32_t>(r)) << 4) + (static_cast<uint32_t>(c) & 7u) * 2u;
+    const uint32_t buf_bytes = static_cast<uint32_t>(nkb2) * A_SLAB_BYTES;
+    const __half2 six = __float2half2_rn(6.0f);
+    int n2 = 0, i = 0;
+    int b = 0, g = 0, j = 0;
+    if (u0 < u1) decode(u0, b, g, j);
+    for (int unit = u0; unit < u1; ++unit, ++i, advance(b, g, j)) {
+      const int s1 = i & 1;
+      mbar_wait(&acc1_full[s1], static_cast<uint32_t>(i >> 1) & 1u);
+      tc_fence_after();
+      // conv1d_1 rows [64 hf, 64 hf + 66) of this channel: read ONCE, reused for every member view of the group
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(s1) * acc1_cols + 64u * hf;
+      uint32_t a0[32], a1[32], a2[2];
+      tmem_ld32(taddr, a0);
+      tmem_ld32(taddr + 32, a1);
+      if (hf == 0) tmem_ld2(taddr + 64, a2); else { a2[0] = 0u; a2[1] = 0u; }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc1_empty[s1]);               // the accumulator stage is free for the unit after next
+      const bool on = 64 * hf < p.t2 - j * FUSE_ROWS;            // the last tile of a clip-view holds 19 block-1 rows
+      for (int mem = p.vg.start[g]; mem < p.vg.start[g + 1]; ++mem, ++n2) {
+        const float gain = p.vg.gain[mem];
+        const int bsel = n2 & 1;
+        mbar_wait(&a2_empty[bsel], (static_cast<uint32_t>(n2 >> 1) & 1u) ^ 1u);   // the MMA of view n2 - 2 has read this buffer
+        if (on) {
+          const uint32_t bo = static_cast<uint32_t>(bsel) * buf_bytes;
+          // y[t] = fp16(relu6(gain * acc + shift)) -- the rounding the unfused path stores -- as packed pairs (y[2i], y[2i+1])
+          auto ypair = [&](int ip) -> uint32_t {
+            const uint32_t lo = ip < 16 ? a0[2 * (ip & 15)] : (ip < 32 ? a1[2 * (ip & 15)] : a2[0]);
+            const uint32_t hi = ip < 16 ? a0[2 * (ip & 15) + 1] : (ip < 32 ? a1[2 * (ip & 15) + 1] : a2[1]);
+            const uint32_t pk = pack_relu_f16x2(fmaf(__uint_as_float(lo), gain, shift), fmaf(__uint_as_float(hi), gain, shift));
+            const __half2 h = __hmin2(*reinterpret_cast<const __half2*>(&pk), six);
+            return *reinterpret_cast<const uint32_t*>(&h);
+          };
+          uint32_t cur = ypair(0);
+#pragma unroll
+          for (int ip = 0; ip < 32; ++ip) {                      // block-1 rows 2 ip, 2 ip + 1 of this half
+            const uint32_t nxt = ypair(ip + 1);
+            // same order as fir3(): tap 0 first, fp32 accumulation, one rounding to fp16
+            const float o0 = fhfma_sel<false, false>(nxt, k2, fhfma_sel<true, true>(cur, k01, fhfma_sel<false, false>(cur, k01, 0.0f)));
+            const float o1 = fhfma_sel<true, false>(nxt, k2, fhfma_sel<false, true>(nxt, k01, fhfma_sel<true, false>(cur, k01, 0.0f)));
+            const uint32_t m8 = static_cast<uint32_t>(ip >> 2) * 8u * ROW_BYTES;          // 8-row group of the half
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(off[(2 * ip) & 7] + bo + m8), "h"(__half_as_ushort(__float2half_rn(o0))) : "memory");
+            asm volatile("st.shared.b16 [%0], %1;" ::"r"(off[(2 * ip + 1) & 7] + bo + m8), "h"(__half_as_ushort(__float2half_rn(o1))) : "memory");
+            cur = nxt;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a2_full[bsel]);              // one arrival per warp
+      }
+    }
+  } else if (!kT && warp < FUSE_MID_WARPS) {
     // =========================== middle: acc1 -> depthwise FIR -> A2 ===========================
     const int q = warp & 3, hf = warp >> 2;                      // TMEM lane quarter, channel half
     const int row = q * 32 + lane;
@@ -1152,7 +1245,7 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
     // =========================== MMA issuer ===========================
     // all 32 lanes walk the loop (uniform control flow and registers); one elected lane issues
     {
-      const uint32_t idesc1 = umma_idesc_f16(TILE_M, p.c0, /*fp16*/ 0);
+      const uint32_t idesc1 = kT ? umma_idesc_f16(p.c0, TILE_M, /*fp16*/ 0) : umma_idesc_f16(TILE_M, p.c0, /*fp16*/ 0);
       const uint32_t idesc2 = umma_idesc_f16(TILE_M, p.c1, /*fp16*/ 0);
       const uint32_t a1 = umma_desc_lo(smem_u32(a1_base)), w1 = umma_desc_lo(smem_u32(w1_base));
       const uint32_t w2 = umma_desc_lo(smem_u32(w2_base)), a2 = umma_desc_lo(smem_u32(a2_base));
@@ -1173,13 +1266,16 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
         mbar_wait(&acc1_empty[s1], (static_cast<uint32_t>(i >> 1) & 1u) ^ 1u);
         mbar_wait(a1_full, ph_a1); ph_a1 ^= 1u;
         tc_fence_after();
-        const uint32_t d = tmem_base + static_cast<uint32_t>(s1 * p.c0);
+        const uint32_t d = tmem_base + static_cast<uint32_t>(s1) * acc1_cols;
+        // kT: the weight image is the A operand (M = c0 channels), the window rows the B operand (N = 128 time steps)
+        const uint32_t xa = kT ? w1 : a1, xb = kT ? a1 : w1;
+        const uint32_t xa_s1 = kT ? w1_slab : (A_SLAB_BYTES >> 4), xb_s1 = kT ? (A_SLAB_BYTES >> 4) : w1_slab;
         if (elect_one()) {
-          umma_f16_lo(d, a1, w1, idesc1, 0u);
-          umma_f16_lo(d, a1 + 2, w1 + 2, idesc1, 1u);
-          umma_f16_lo(d, a1 + 4, w1 + 4, idesc1, 1u);
-          umma_f16_lo(d, a1 + 6, w1 + 6, idesc1, 1u);
-          umma_f16_lo(d, a1 + (A_SLAB_BYTES >> 4), w1 + w1_slab, idesc1, 1u);   // samples 64..79
+          umma_f16_lo(d, xa, xb, idesc1, 0u);
+          umma_f16_lo(d, xa + 2, xb + 2, idesc1, 1u);
+          umma_f16_lo(d, xa + 4, xb + 4, idesc1, 1u);
+          umma_f16_lo(d, xa + 6, xb + 6, idesc1, 1u);
+          umma_f16_lo(d, xa + xa_s1, xb + xb_s1, idesc1, 1u);      // samples 64..79
           umma_commit(a1_empty);
           umma_commit(&acc1_full[s1]);
         }
@@ -1281,6 +1377,13 @@ EncodeTiledFn encode_tiled_fn() {
 // fp16 channels-last activation [d2][d1][c] (d2 = 1 for a plain [rows, c] matrix); box = [1][box_rows][64 ch]
 int make_tensor_map(kws_handle* h, CUtensorMap* tm, const __half* act, int c, long long d1, long long d2,
                     int box_rows, bool swizzle128, int box_ch = SLAB_K) {
+  static_assert(sizeof(CUtensorMap) == 128, "tensor map cache entry size");
+  for (const auto& e : h->tmap_cache)
+    if (e.act == act && e.c == c && e.d1 == d1 && e.d2 == d2 && e.box_rows == box_rows && e.swizzle == (swizzle128 ? 1 : 0) &&
+        e.box_ch == box_ch) {
+      memcpy(tm, e.map, sizeof(CUtensorMap));
+      return KWS_OK;
+    }
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return fail(h, KWS_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint32_t rank = d2 > 1 ? 3 : 2;
@@ -1294,6 +1397,10 @@ int make_tensor_map(kws_handle* h, CUtensorMap* tm, const __half* act, int c, lo
                         swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(h, KWS_ECUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(r));
+  if (h->tmap_cache.size() >= 256) h->tmap_cache.clear();          // ragged batch sizes: start over rather than grow
+  kws_handle::TmapEntry e{act, c, d1, d2, box_rows, swizzle128 ? 1 : 0, box_ch, {}};
+  memcpy(e.map, tm, sizeof(CUtensorMap));
+  h->tmap_cache.push_back(e);
   return KWS_OK;
 }
 
@@ -1478,13 +1585,18 @@ int launch_conv1_block1(kws_handle* h, Model& m, const float* wav, int nb, const
   const FusedSmem lay = fused_smem(p.c0, p.c1);
   if (static_cast<int>(lay.total) > SMEM_LIMIT) return fail(h, KWS_EUNSUPPORTED, "fused conv1d_1 + block 1 does not fit in shared memory");
   if (!(h->smem_attr_done & 16u)) {
-    KWS_CUDA(h, cudaFuncSetAttribute(conv1_block1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    KWS_CUDA(h, cudaFuncSetAttribute(conv1_block1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    KWS_CUDA(h, cudaFuncSetAttribute(conv1_block1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     h->smem_attr_done |= 16u;
   }
   const int grid = std::min(p.num_units, h->num_sms);
   if (grid <= 0) return KWS_OK;
+  // c0 == 128: the transposed form (see the kernel); KWS_FUSE_V1=1 keeps the r01 row-major form for A/B runs
+  static const bool v1 = [] { const char* e = getenv("KWS_FUSE_V1"); return e && e[0] == '1'; }();
+  const bool transposed = !v1 && p.c0 == TILE_M;
   KWS_T0(h, KC_CONV1, st);
-  conv1_block1_kernel<<<grid, FUSE_THREADS, lay.total, st>>>(p);
+  if (transposed) conv1_block1_kernel<true><<<grid, FUSE_THREADS, lay.total, st>>>(p);
+  else conv1_block1_kernel<false><<<grid, FUSE_THREADS, lay.total, st>>>(p);
   KWS_T1(h, st);
   if (debug_sync() && cudaDeviceSynchronize() != cudaSuccess)
     return fail(h, KWS_ECUDA, std::string("conv1_block1_kernel: ") + cudaGetErrorString(cudaGetLastError()));
@@ -1557,6 +1669,7 @@ int launch_forward_tc(kws_handle* h, Model& m, const float* wav, int B, const Vi
   const int clips_per_chunk = std::max(1, h->max_rows / V);
   const size_t need = static_cast<size_t>(clips_per_chunk) * V * m.max_act_elems * sizeof(__half);
   if (h->act_bytes < need) {
+    h->tmap_cache.clear();
     for (int i = 0; i < 2; ++i) {
       if (h->act[i]) cudaFree(h->act[i]);
       h->act[i] = nullptr;
