@@ -33,14 +33,35 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // Persistent kernel: the dense_1 (166 KB) and dense_2 (48 KB, transposed) weights live in shared
 // memory for the whole launch -- re-fetching them per clip-view from L2 is what bounds a
-// one-CTA-per-clip formulation -- and every warp owns one (clip, view) at a time: lane-strided dot
-// products (bank-conflict-free: the row stride of dense_1 is 9 words), warp-shuffle reductions,
-// pooled features in registers.  The stage is bound by shared-memory bandwidth (166 KB of dense_1
-// weights per clip-view), so a warp takes IPW consecutive views of one clip at a time and reuses
+// one-CTA-per-clip formulation -- and every warp owns IPW consecutive views of one clip at a time and reuses
 // every weight it reads for all of them.  A CTA iteration covers floor(16 * IPW / n_views) clips;
 // the per-view probabilities meet in shared memory and are averaged in view order.
+//
+// r02: a lane owns 8 CONSECUTIVE channels (one 16-byte load of the fp16 activation) instead of every 32nd element
+// (a 2-byte load: r01 spent the kernel waiting for 576 of them per lane and 4 views, 0.11 of the HBM roofline).
+// The flattened activation index is i = 256 k + 8 lane + e; dense_1's rows are re-laid out in shared memory as
+// [k][e][j 0..3 | j 4..7 | j 8][lane] so that the nine weights of an element are two conflict-free LDS.128 and one
+// LDS.32.  The next block's activations are in flight (as raw 16-byte words) while the current block is multiplied.
 constexpr int HEAD_WARPS = 16;
-constexpr int HEAD_CH_PER_LANE = 16;              // channels per lane in the pooling: C <= 512
+constexpr int HEAD_BLK = 256;                       // activation elements per block: 32 lanes x 8
+constexpr int HEAD_WROW = 2 * 128 + 32;             // floats of one (k, e) weight row group: j0-3 | j4-7 | j8, each x 32 lanes
+constexpr int HEAD_MAX_KB = 2;                      // channel blocks of 256 in the pooling: C <= 512
+
+template <typename TAct> struct Raw8;
+template <> struct Raw8<__half> { uint4 v; };
+template <> struct Raw8<float> { float4 a, b; };
+__device__ __forceinline__ void load_raw8(const __half* p, Raw8<__half>& r) { r.v = __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void load_raw8(const float* p, Raw8<float>& r) {
+  r.a = __ldg(reinterpret_cast<const float4*>(p)); r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+}
+__device__ __forceinline__ void unpack8(const Raw8<__half>& r, float (&x)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&r.v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); x[2 * i] = f.x; x[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ void unpack8(const Raw8<float>& r, float (&x)[8]) {
+  x[0] = r.a.x; x[1] = r.a.y; x[2] = r.a.z; x[3] = r.a.w; x[4] = r.b.x; x[5] = r.b.y; x[6] = r.b.z; x[7] = r.b.w;
+}
 
 template <typename TAct, int IPW>
 __global__ void __launch_bounds__(HEAD_WARPS * 32, 1)
@@ -49,20 +70,22 @@ head_kernel(const TAct* __restrict__ act, int C, int n_views, int n_clips, const
             int pool_max_avg, float* __restrict__ probs_mean, int32_t* __restrict__ argmax) {
   extern __shared__ float sm[];
   const int n = HEAD_T * C;
+  const int nblk = (n + HEAD_BLK - 1) / HEAD_BLK;
   const int feat = pool_max_avg ? 2 * C : C;
-  float* w1 = sm;                                       // [n][HEAD_T]
-  float* w2t = w1 + n * HEAD_T;                         // [classes][feat]
+  float* w1 = sm;                                       // [nblk][8][HEAD_WROW]
+  float* w2t = w1 + nblk * 8 * HEAD_WROW;               // [classes][feat]
   float* pv = w2t + classes * feat;                     // [clips per iteration][n_views][32] per-view probabilities
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  {
-    const float4* src = reinterpret_cast<const float4*>(w_d1);
-    float4* dst = reinterpret_cast<float4*>(w1);
-    for (int i = tid; i < n * HEAD_T / 4; i += HEAD_WARPS * 32) dst[i] = __ldg(&src[i]);
-    for (int i = tid; i < feat * classes; i += HEAD_WARPS * 32) {
-      const int r = i / classes, j = i - r * classes;
-      w2t[j * feat + r] = __ldg(&w_d2[i]);
-    }
+  for (int idx = tid; idx < n * HEAD_T; idx += HEAD_WARPS * 32) {          // dense_1 [n][9] -> [k][e][j groups][lane]
+    const int i = idx / HEAD_T, j = idx - i * HEAD_T;
+    const int k = i / HEAD_BLK, r = i - k * HEAD_BLK, ln = r >> 3, e = r & 7;
+    float* row = w1 + (k * 8 + e) * HEAD_WROW;
+    row[j < 4 ? ln * 4 + j : (j < 8 ? 128 + ln * 4 + (j - 4) : 256 + ln)] = __ldg(&w_d1[idx]);
+  }
+  for (int i = tid; i < feat * classes; i += HEAD_WARPS * 32) {
+    const int r = i / classes, j = i - r * classes;
+    w2t[j * feat + r] = __ldg(&w_d2[i]);
   }
   const float bias = lane < HEAD_T ? __ldg(&b_d1[lane]) : 0.0f;
   __syncthreads();
@@ -80,17 +103,37 @@ head_kernel(const TAct* __restrict__ act, int C, int n_views, int n_clips, const
       for (int u = 0; u < IPW; ++u)
 #pragma unroll
         for (int j = 0; j < HEAD_T; ++j) p[u][j] = 0.0f;
-#pragma unroll 8                                         // 8 x IPW activation loads in flight per lane
-      for (int i = lane; i < n; i += 32) {
-        float xv[IPW];
+      Raw8<TAct> nxt[IPW];
+      if (8 * lane < n) {
 #pragma unroll
-        for (int u = 0; u < IPW; ++u) xv[u] = to_float(x0[static_cast<size_t>(u) * n + i]);
-        const float* wr = w1 + i * HEAD_T;
+        for (int u = 0; u < IPW; ++u) load_raw8(x0 + static_cast<size_t>(u) * n + 8 * lane, nxt[u]);
+      }
+      for (int k = 0; k < nblk; ++k) {
+        const int i0 = HEAD_BLK * k + 8 * lane;
+        float xa[IPW][8];
 #pragma unroll
-        for (int j = 0; j < HEAD_T; ++j) {
-          const float w = wr[j];
+        for (int u = 0; u < IPW; ++u) unpack8(nxt[u], xa[u]);
+        if (i0 + HEAD_BLK < n) {                          // the next block's loads fly under this block's FMAs
 #pragma unroll
-          for (int u = 0; u < IPW; ++u) p[u][j] = fmaf(xv[u], w, p[u][j]);
+          for (int u = 0; u < IPW; ++u) load_raw8(x0 + static_cast<size_t>(u) * n + i0 + HEAD_BLK, nxt[u]);
+        }
+        if (i0 < n) {
+          const float* wk = w1 + k * 8 * HEAD_WROW + lane * 4;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float4 wa = *reinterpret_cast<const float4*>(wk + e * HEAD_WROW);
+            const float4 wb = *reinterpret_cast<const float4*>(wk + e * HEAD_WROW + 128);
+            const float w8 = w1[(k * 8 + e) * HEAD_WROW + 256 + lane];
+#pragma unroll
+            for (int u = 0; u < IPW; ++u) {
+              const float xv = xa[u][e];
+              p[u][0] = fmaf(xv, wa.x, p[u][0]); p[u][1] = fmaf(xv, wa.y, p[u][1]);
+              p[u][2] = fmaf(xv, wa.z, p[u][2]); p[u][3] = fmaf(xv, wa.w, p[u][3]);
+              p[u][4] = fmaf(xv, wb.x, p[u][4]); p[u][5] = fmaf(xv, wb.y, p[u][5]);
+              p[u][6] = fmaf(xv, wb.z, p[u][6]); p[u][7] = fmaf(xv, wb.w, p[u][7]);
+              p[u][8] = fmaf(xv, w8, p[u][8]);
+            }
+          }
         }
       }
 #pragma unroll
@@ -110,27 +153,40 @@ head_kernel(const TAct* __restrict__ act, int C, int n_views, int n_clips, const
         float att[HEAD_T];
 #pragma unroll
         for (int t = 0; t < HEAD_T; ++t) att[t] = __shfl_sync(0xffffffffu, a, t);
-        // ---- multiply_1 + pooling: lane owns channels lane, lane + 32, ... ----
-        float z0[HEAD_CH_PER_LANE], z1[HEAD_CH_PER_LANE];
+        // ---- multiply_1 + pooling: lane owns channels 256 kb + 8 lane .. + 7 ----
+        float z0[HEAD_MAX_KB * 8], z1[HEAD_MAX_KB * 8];
 #pragma unroll
-        for (int k = 0; k < HEAD_CH_PER_LANE; ++k) {
-          const int c = lane + 32 * k;
-          z0[k] = 0.0f; z1[k] = 0.0f;
-          if (c < C) {
-            float m = -INFINITY, sum_x = 0.0f, sum_w = 0.0f;
+        for (int kb = 0; kb < HEAD_MAX_KB; ++kb) {
+          const int c0 = HEAD_BLK * kb + 8 * lane;
+          float m[8], sum_x[8], sum_w[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { m[q] = -INFINITY; sum_x[q] = 0.0f; sum_w[q] = 0.0f; }
+          if (c0 < C) {
 #pragma unroll
             for (int t = 0; t < HEAD_T; ++t) {
-              const float xv = to_float(x[t * C + c]);
-              const float wv = __fmul_rn(xv, att[t]);          // multiply_1
-              m = fmaxf(m, wv);
-              sum_x += xv;
-              sum_w += wv;
+              Raw8<TAct> r;
+              load_raw8(x + t * C + c0, r);
+              float xv[8];
+              unpack8(r, xv);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float wv = __fmul_rn(xv[q], att[t]);       // multiply_1
+                m[q] = fmaxf(m[q], wv);
+                sum_x[q] += xv[q];
+                sum_w[q] += wv;
+              }
             }
-            if (pool_max_avg) {
-              z0[k] = m;                                       // global_max_pooling1d_1(x * a)
-              z1[k] = __fdiv_rn(sum_x, static_cast<float>(HEAD_T));   // global_average_pooling1d_1(x)
-            } else {
-              z0[k] = __fdiv_rn(sum_w, static_cast<float>(HEAD_T));   // exp 106: mean_t(x * a)
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            z0[kb * 8 + q] = 0.0f; z1[kb * 8 + q] = 0.0f;
+            if (c0 < C) {
+              if (pool_max_avg) {
+                z0[kb * 8 + q] = m[q];                                              // global_max_pooling1d_1(x * a)
+                z1[kb * 8 + q] = __fdiv_rn(sum_x[q], static_cast<float>(HEAD_T));   // global_average_pooling1d_1(x)
+              } else {
+                z0[kb * 8 + q] = __fdiv_rn(sum_w[q], static_cast<float>(HEAD_T));   // exp 106: mean_t(x * a)
+              }
             }
           }
         }
@@ -140,11 +196,19 @@ head_kernel(const TAct* __restrict__ act, int C, int n_views, int n_clips, const
           const float* wc = w2t + j * feat;
           float d = 0.0f;
 #pragma unroll
-          for (int k = 0; k < HEAD_CH_PER_LANE; ++k) {
-            const int c = lane + 32 * k;
-            if (c < C) {
-              d = fmaf(z0[k], wc[c], d);
-              if (pool_max_avg) d = fmaf(z1[k], wc[C + c], d);
+          for (int kb = 0; kb < HEAD_MAX_KB; ++kb) {
+            const int c0 = HEAD_BLK * kb + 8 * lane;
+            if (c0 < C) {
+              const float4 wa = *reinterpret_cast<const float4*>(wc + c0), wb = *reinterpret_cast<const float4*>(wc + c0 + 4);
+              const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+              for (int q = 0; q < 8; ++q) d = fmaf(z0[kb * 8 + q], w[q], d);
+              if (pool_max_avg) {
+                const float4 va = *reinterpret_cast<const float4*>(wc + C + c0), vb = *reinterpret_cast<const float4*>(wc + C + c0 + 4);
+                const float v[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+                for (int q = 0; q < 8; ++q) d = fmaf(z1[kb * 8 + q], v[q], d);
+              }
             }
           }
           d = warp_sum(d);
@@ -205,11 +269,12 @@ int launch_head(kws_handle* h, Model& m, const void* act, bool act_half, int n_c
   if (m.classes > HEAD_MAX_CLASSES) return fail(h, KWS_EUNSUPPORTED, "too many classes");
   if (n_views < 1 || n_views > HEAD_WARPS) return fail(h, KWS_EINVAL, "n_views must be in 1..16");
   const int C = m.c_last;
-  if (C > 32 * HEAD_CH_PER_LANE || C % 4) return fail(h, KWS_EUNSUPPORTED, "head expects at most 512 channels");
+  if (C > HEAD_MAX_KB * HEAD_BLK || C % 8) return fail(h, KWS_EUNSUPPORTED, "head expects at most 512 channels, a multiple of 8");
   const int feat = m.pool_max_avg ? 2 * C : C;
   const int ipw = n_views % 4 == 0 ? 4 : (n_views % 2 == 0 ? 2 : 1);   // views per warp (weights reused from registers)
   const int cpi = HEAD_WARPS / (n_views / ipw);
-  const size_t smem = (static_cast<size_t>(HEAD_T) * C * HEAD_T + static_cast<size_t>(m.classes) * feat +
+  const int nblk = (HEAD_T * C + HEAD_BLK - 1) / HEAD_BLK;
+  const size_t smem = (static_cast<size_t>(nblk) * 8 * HEAD_WROW + static_cast<size_t>(m.classes) * feat +
                        static_cast<size_t>(cpi) * n_views * 32) * sizeof(float);
   if (smem > 227 * 1024) return fail(h, KWS_EUNSUPPORTED, "head weights do not fit in shared memory");
   const int grid = std::max(1, std::min(h->num_sms, (n_clips + cpi - 1) / cpi));

@@ -332,6 +332,49 @@ __device__ __forceinline__ void umma_slab4_commit(uint32_t tmem_d, uint32_t a_lo
       "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate_first), "r"(bar1), "r"(bar2), "r"(UMMA_DESC_HI)
       : "memory");
 }
+// Same for an A operand in the MN-major SW128 layout (rows = one k value x 64 contiguous M elements, 8 k per 1024-byte
+// atom, LBO between the 64-element M blocks, SBO between the 8-k groups): the K = 16 steps of a slab advance the A start
+// address by a_step (= 2 SBO, in 16-byte units) and the A descriptor has its own high word.
+__device__ __forceinline__ uint32_t umma_desc_lo_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+__host__ __device__ constexpr uint32_t umma_desc_hi_mn(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ void umma_slab4_commit_mn(uint32_t tmem_d, uint32_t a_lo, uint32_t a_step, uint32_t a_hi, uint32_t b_lo,
+                                                     uint32_t idesc, uint32_t accumulate_first, uint32_t bar1, uint32_t bar2) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe, pa, pt, p1, p2;\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .b32 ax, bx;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "setp.eq.b32 pt, 0, 0;\n\t"
+      "setp.ne.and.b32 p1, %5, 0, pe;\n\t"
+      "setp.ne.and.b32 p2, %6, 0, pe;\n\t"
+      "mov.b64 da, {%1, %9};\n\t"
+      "mov.b64 db, {%2, %7};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pa;\n\t"
+      "add.u32 ax, %1, %8;\n\t"
+      "add.u32 bx, %2, 2;\n\t"
+      "mov.b64 da, {ax, %9};\n\t"
+      "mov.b64 db, {bx, %7};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "add.u32 ax, ax, %8;\n\t"
+      "add.u32 bx, %2, 4;\n\t"
+      "mov.b64 da, {ax, %9};\n\t"
+      "mov.b64 db, {bx, %7};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "add.u32 ax, ax, %8;\n\t"
+      "add.u32 bx, %2, 6;\n\t"
+      "mov.b64 da, {ax, %9};\n\t"
+      "mov.b64 db, {bx, %7};\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+      "@p1 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t"
+      "@p2 tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate_first), "r"(bar1), "r"(bar2), "r"(UMMA_DESC_HI), "r"(a_step), "r"(a_hi)
+      : "memory");
+}
 // same with a run-time number of K steps (1..4): the last K slab of a contraction whose K is not a multiple of 64
 __device__ __forceinline__ void umma_slab_commit(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
                                                  uint32_t accumulate_first, uint32_t ksteps, uint32_t bar1, uint32_t bar2) {

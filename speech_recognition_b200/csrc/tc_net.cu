@@ -393,24 +393,28 @@ struct Conv1ProducerT {
 template <bool kGain>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const float* s_shift32, uint8_t* row_base,
                                                int ch0, int sw, float gain) {
+  // Every shift is loaded BEFORE the first store: row_base is a byte pointer and may alias anything, so a load placed
+  // after a store to it cannot be hoisted by the compiler, and the warp would wait out one shared-memory round trip per
+  // 16-byte chunk (r02c profile of the fused kernel's output warps: 0.12 instructions per cycle, short-scoreboard bound).
+  float4 sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sh[i] = *reinterpret_cast<const float4*>(s_shift32 + 4 * i);
   const __half2 six = __float2half2_rn(6.0f);
+  uint32_t o[16];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint32_t o[4];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const float4 sh = *reinterpret_cast<const float4*>(s_shift32 + 8 * q + 4 * e);
-      const float f0 = __uint_as_float(v[8 * q + 4 * e]), f1 = __uint_as_float(v[8 * q + 4 * e + 1]);
-      const float f2 = __uint_as_float(v[8 * q + 4 * e + 2]), f3 = __uint_as_float(v[8 * q + 4 * e + 3]);
-      const uint32_t a = kGain ? pack_relu_f16x2(fmaf(f0, gain, sh.x), fmaf(f1, gain, sh.y)) : pack_relu_f16x2(f0 + sh.x, f1 + sh.y);
-      const uint32_t b = kGain ? pack_relu_f16x2(fmaf(f2, gain, sh.z), fmaf(f3, gain, sh.w)) : pack_relu_f16x2(f2 + sh.z, f3 + sh.w);
-      const __half2 ha = __hmin2(*reinterpret_cast<const __half2*>(&a), six);
-      const __half2 hb = __hmin2(*reinterpret_cast<const __half2*>(&b), six);
-      o[2 * e] = *reinterpret_cast<const uint32_t*>(&ha);
-      o[2 * e + 1] = *reinterpret_cast<const uint32_t*>(&hb);
-    }
-    *reinterpret_cast<uint4*>(row_base + (((ch0 + q) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+  for (int i = 0; i < 8; ++i) {
+    const float f0 = __uint_as_float(v[4 * i]), f1 = __uint_as_float(v[4 * i + 1]);
+    const float f2 = __uint_as_float(v[4 * i + 2]), f3 = __uint_as_float(v[4 * i + 3]);
+    const uint32_t a = kGain ? pack_relu_f16x2(fmaf(f0, gain, sh[i].x), fmaf(f1, gain, sh[i].y)) : pack_relu_f16x2(f0 + sh[i].x, f1 + sh[i].y);
+    const uint32_t b = kGain ? pack_relu_f16x2(fmaf(f2, gain, sh[i].z), fmaf(f3, gain, sh[i].w)) : pack_relu_f16x2(f2 + sh[i].z, f3 + sh[i].w);
+    const __half2 ha = __hmin2(*reinterpret_cast<const __half2*>(&a), six);
+    const __half2 hb = __hmin2(*reinterpret_cast<const __half2*>(&b), six);
+    o[2 * i] = *reinterpret_cast<const uint32_t*>(&ha);
+    o[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&hb);
   }
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<uint4*>(row_base + (((ch0 + q) ^ sw) << 4)) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
 }
 
 // Event log for pipeline analysis (KWS_TRACE=<block index>, tools/gpu_trace.sh, tools/trace_view.py): role r
@@ -900,9 +904,18 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
 constexpr int FUSE_ROWS = TILE_M - 2;                            // block-1 rows per tile
 // 16 warps = 512 threads: the register file then allows 128 registers per thread (the middle warps are the
 // critical role and spill at 96)
-constexpr int FUSE_MID_WARPS = 8, FUSE_OUT_WARP0 = 8, FUSE_OUT_WARPS = 4, FUSE_MMA_WARP = 12, FUSE_PROD_WARP0 = 13;
-constexpr int FUSE_PROD_THREADS = 96;
-constexpr int FUSE_THREADS = 32 * FUSE_PROD_WARP0 + FUSE_PROD_THREADS;   // 512
+constexpr int FUSE_MID_WARPS = 8, FUSE_OUT_WARP0 = 8, FUSE_PROD_THREADS = 96;
+// 16 warps = 512 threads, so that every role may use up to 128 registers (the middle warps need them).  (r02d tried
+// 20 warps -- 8 output warps -- with setmaxnreg re-balancing: an inc can only take registers that a dec of the SAME CTA
+// released, the launch-time slack of the register file is not in that pool, and the kernel dead-locked.)
+template <bool kT> struct FuseRoles {
+  static constexpr int OUT_WARPS = 4;
+  static constexpr int MMA_WARP = FUSE_OUT_WARP0 + OUT_WARPS;
+  static constexpr int PROD_WARP0 = MMA_WARP + 1;
+  static constexpr int THREADS = 32 * PROD_WARP0 + FUSE_PROD_THREADS;   // 512
+};
+constexpr uint32_t FUSE_A2_LBO = 1024, FUSE_A2_SBO = 2048;        // transposed form: MN-major A2 (see the middle warps)
+constexpr int FUSE_OUT_BOX_BYTES = 8 * OUT_STAGE_BYTES;          // 4 warps x 2 boxes, or 8 warps x 1 box
 
 struct alignas(64) FusedParams {
   CUtensorMap tmap_out;      // block-1 output, 3-D [clip-views, t2, c1], box [64 ch, 32 rows, 1], 128-byte swizzle
@@ -931,7 +944,7 @@ __host__ __device__ inline FusedSmem fused_smem(int c0, int c1) {
   // operand of the pointwise GEMM; view v + 1 is packed and filtered in the other buffer while the MMA reads this one
   s.a2 = o; o += 2u * static_cast<uint32_t>(c0 / SLAB_K) * A_SLAB_BYTES;
   s.raw = s.a2;
-  s.out = o; o += FUSE_OUT_WARPS * OUT_STAGE_BYTES;                      // (the FIR of the last rows reads 2 rows past a raw slab: into the next region)
+  s.out = o; o += FUSE_OUT_BOX_BYTES;                                    // (the r01 FIR of the last rows reads 2 rows past a raw slab: into this region)
   s.win = o; o += 2 * CONV1_WIN_BYTES;
   s.sh1 = o; o += c0 * 4u;
   s.sh2 = o; o += c1 * 4u;
@@ -984,8 +997,10 @@ __device__ __forceinline__ float fhfma_sel(uint32_t a, uint32_t b, float c) {
 // accumulator of a (clip, view group, tile) unit is read from TMEM ONCE into registers and reused for every member
 // view of the group (TMEM reads are 64 B / cycle / SM; re-reading it per view was a third of the kernel's floor).
 template <bool kT>
-__global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __grid_constant__ FusedParams p) {
+__global__ void __launch_bounds__(FuseRoles<kT>::THREADS, 1) conv1_block1_kernel(const __grid_constant__ FusedParams p) {
   extern __shared__ uint8_t smem_raw[];
+  constexpr int FUSE_OUT_WARPS = FuseRoles<kT>::OUT_WARPS, FUSE_MMA_WARP = FuseRoles<kT>::MMA_WARP,
+                FUSE_PROD_WARP0 = FuseRoles<kT>::PROD_WARP0, FUSE_THREADS = FuseRoles<kT>::THREADS;
   const FusedSmem lay = fused_smem(p.c0, p.c1);
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a1_base = smem + lay.a1;
@@ -1065,12 +1080,13 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
     const uint32_t k01 = static_cast<uint32_t>(__half_as_ushort(s_taps[c])) |
                          (static_cast<uint32_t>(__half_as_ushort(s_taps[p.c0 + c])) << 16);     // taps 0, 1 of this channel
     const uint32_t k2 = static_cast<uint32_t>(__half_as_ushort(s_taps[2 * p.c0 + c]));           // tap 2
-    // A2[t][c] in the K-major SW128 slabs of the pointwise GEMM: slab c / 64, row t, 16-byte chunk ((c % 64) / 8) ^ (t % 8)
-    uint32_t off[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r)
-      off[r] = smem_u32(a2_base) + static_cast<uint32_t>(c >> 6) * A_SLAB_BYTES + static_cast<uint32_t>(64 * hf + r) * ROW_BYTES +
-               ((((static_cast<uint32_t>(c) & 63u) >> 3) ^ static_cast<uint32_t>(r)) << 4) + (static_cast<uint32_t>(c) & 7u) * 2u;
+    // A2 is written in the MN-major SW128 operand layout: a 128-byte row holds 64 consecutive time steps of ONE channel
+    // (8 channels per 1024-byte atom, chunk j of a row at position j ^ (c % 8)), atom (c / 8, time half) at
+    // (c / 8) * 2048 + half * 1024.  This thread's 64 outputs are exactly one row: 8 conflict-free 16-byte stores
+    // instead of 64 scattered 2-byte ones (K-major A2 in r02b/c: 1.4 shared-memory wavefronts per 2-byte store).
+    const uint32_t row_addr = smem_u32(a2_base) + static_cast<uint32_t>(c >> 3) * FUSE_A2_SBO + static_cast<uint32_t>(hf) * FUSE_A2_LBO +
+                              (static_cast<uint32_t>(c) & 7u) * ROW_BYTES;
+    const uint32_t csw = static_cast<uint32_t>(c) & 7u;
     const uint32_t buf_bytes = static_cast<uint32_t>(nkb2) * A_SLAB_BYTES;
     const __half2 six = __float2half2_rn(6.0f);
     int n2 = 0, i = 0;
@@ -1107,15 +1123,19 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
           };
           uint32_t cur = ypair(0);
 #pragma unroll
-          for (int ip = 0; ip < 32; ++ip) {                      // block-1 rows 2 ip, 2 ip + 1 of this half
-            const uint32_t nxt = ypair(ip + 1);
-            // same order as fir3(): tap 0 first, fp32 accumulation, one rounding to fp16
-            const float o0 = fhfma_sel<false, false>(nxt, k2, fhfma_sel<true, true>(cur, k01, fhfma_sel<false, false>(cur, k01, 0.0f)));
-            const float o1 = fhfma_sel<true, false>(nxt, k2, fhfma_sel<false, true>(nxt, k01, fhfma_sel<true, false>(cur, k01, 0.0f)));
-            const uint32_t m8 = static_cast<uint32_t>(ip >> 2) * 8u * ROW_BYTES;          // 8-row group of the half
-            asm volatile("st.shared.b16 [%0], %1;" ::"r"(off[(2 * ip) & 7] + bo + m8), "h"(__half_as_ushort(__float2half_rn(o0))) : "memory");
-            asm volatile("st.shared.b16 [%0], %1;" ::"r"(off[(2 * ip + 1) & 7] + bo + m8), "h"(__half_as_ushort(__float2half_rn(o1))) : "memory");
-            cur = nxt;
+          for (int jc = 0; jc < 8; ++jc) {                       // 16-byte chunk jc = block-1 rows 8 jc .. 8 jc + 7 of this half
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t nxt = ypair(4 * jc + e + 1);
+              // same order as fir3(): tap 0 first, fp32 accumulation, one rounding to fp16
+              const float o0 = fhfma_sel<false, false>(nxt, k2, fhfma_sel<true, true>(cur, k01, fhfma_sel<false, false>(cur, k01, 0.0f)));
+              const float o1 = fhfma_sel<true, false>(nxt, k2, fhfma_sel<false, true>(nxt, k01, fhfma_sel<true, false>(cur, k01, 0.0f)));
+              o[e] = pack_f16x2(o0, o1);
+              cur = nxt;
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + bo + ((static_cast<uint32_t>(jc) ^ csw) << 4)),
+                         "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
           }
         }
         fence_proxy_async_smem();
@@ -1200,12 +1220,16 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
     }
   } else if (warp < FUSE_MMA_WARP) {
     // =========================== output: acc2 -> BN shift, ReLU6 -> TMA store ===========================
+    // This is the role every other one ends up waiting for (r02c profile: 83 % busy at 0.12 instructions per cycle, the
+    // middle warps 39 %): one warp cannot hide its own TMEM / shared-memory / ALU latencies.  So: kColGroups warps per
+    // TMEM lane quarter, each on every kColGroups-th 64-column chunk; both 32-column halves of a chunk are loaded
+    // before the first wait; the accumulator stage is handed back as soon as its columns are in registers.
+    constexpr int kColGroups = FUSE_OUT_WARPS / 4, kBoxes = 8 / FUSE_OUT_WARPS;
     const int ow = warp - FUSE_OUT_WARP0;
     const int q = ow & 3, c_first = (ow >> 2) * 64;              // TMEM lane quarter; first 64-column chunk
-    constexpr int c_step = 64 * (FUSE_OUT_WARPS / 4);
-    uint8_t* box = out_base + ow * OUT_STAGE_BYTES;               // one store box per warp
-    uint8_t* row_base = box + lane * ROW_BYTES;
-    int n2 = 0;
+    constexpr int c_step = 64 * kColGroups;
+    uint8_t* box0 = out_base + ow * kBoxes * OUT_STAGE_BYTES;
+    int ob = 0, n2 = 0;
     if (lane == 0) { tma_prefetch_desc(&p.tmap_out); tma_prefetch_desc(&p.tmap_out30); }
     int b = 0, g = 0, j = 0;
     if (u0 < u1) decode(u0, b, g, j);
@@ -1215,29 +1239,36 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
         const int s2 = n2 & 1;
         mbar_wait(&acc2_full[s2], static_cast<uint32_t>(n2 >> 1) & 1u);
         tc_fence_after();
-        if (row0 < p.t2) {
+        if (row0 < p.t2 && c_first < p.c1) {
           const int rv = b * p.n_views + p.vg.view[mem];
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc2_col0 + static_cast<uint32_t>(s2 * p.c1);
+          uint32_t va[32], vb[32];
+          tmem_ld32(taddr + c_first, va);
+          tmem_ld32(taddr + c_first + 32, vb);
           for (int c0 = c_first; c0 < p.c1; c0 += c_step) {
-            uint32_t va[32];                                     // one 32-column buffer keeps the kernel under 80 registers
-            tmem_ld32(taddr + c0, va);
-            if (lane == 0) bulk_wait_group_read<0>();            // the previous store has read the box
+            uint8_t* box = box0 + ob * OUT_STAGE_BYTES;
+            uint8_t* row_base = box + lane * ROW_BYTES;
+            if (lane == 0) bulk_wait_group_read<kBoxes - 1>();   // the store that last used this box has read it
             __syncwarp();
             tmem_ld_wait();
+            const bool more = c0 + c_step < p.c1;
+            if (!more) { tc_fence_before(); mbar_arrive(&acc2_empty[s2]); }   // every column of this view is in registers
             epilogue_chunk<false>(va, s_sh2 + c0, row_base, 0, lane & 7, 1.0f);
-            tmem_ld32(taddr + c0 + 32, va);
-            tmem_ld_wait();
-            epilogue_chunk<false>(va, s_sh2 + c0 + 32, row_base, 4, lane & 7, 1.0f);
+            if (more) tmem_ld32(taddr + c0 + c_step, va);
+            epilogue_chunk<false>(vb, s_sh2 + c0 + 32, row_base, 4, lane & 7, 1.0f);
+            if (more) tmem_ld32(taddr + c0 + c_step + 32, vb);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
               tma_store_3d(q == 3 ? &p.tmap_out30 : &p.tmap_out, c0, row0, rv, box);
               bulk_commit_group();
             }
+            ob = (ob + 1) & (kBoxes - 1);
           }
+        } else {
+          tc_fence_before();
+          mbar_arrive(&acc2_empty[s2]);
         }
-        tc_fence_before();
-        mbar_arrive(&acc2_empty[s2]);
       }
     }
     if (lane == 0) bulk_wait_group_all();
@@ -1295,6 +1326,13 @@ __global__ void __launch_bounds__(FUSE_THREADS, 1) conv1_block1_kernel(const __g
           tc_fence_after();
           const uint32_t d = tmem_base + acc2_col0 + static_cast<uint32_t>(s2 * p.c1);
           uint32_t a = a2 + static_cast<uint32_t>(s2) * a2_buf_lo, w = w2;
+          if constexpr (kT) {
+            // A2 is MN-major (see the middle warps): a K = 16 step spans two 8-channel groups = 2 SBO, a 64-channel slab 8 SBO
+            a = umma_desc_lo_mn(smem_u32(a2_base), FUSE_A2_LBO) + static_cast<uint32_t>(s2) * a2_buf_lo;
+            for (int kb = 0; kb < nkb2; ++kb, a += (8 * FUSE_A2_SBO) >> 4, w += w2_slab)
+              umma_slab4_commit_mn(d, a, (2 * FUSE_A2_SBO) >> 4, umma_desc_hi_mn(FUSE_A2_SBO), w, idesc2 | (1u << 15), kb != 0 ? 1u : 0u,
+                                   kb == nkb2 - 1 ? a2_empty0 + 8u * s2 : 0u, kb == nkb2 - 1 ? acc2_full0 + 8u * s2 : 0u);
+          } else
           for (int kb = 0; kb < nkb2; ++kb, a += A_SLAB_BYTES >> 4, w += w2_slab)
             umma_slab4_commit(d, a, w, idesc2, kb != 0 ? 1u : 0u, kb == nkb2 - 1 ? a2_empty0 + 8u * s2 : 0u,
                               kb == nkb2 - 1 ? acc2_full0 + 8u * s2 : 0u);
@@ -1595,8 +1633,8 @@ int launch_conv1_block1(kws_handle* h, Model& m, const float* wav, int nb, const
   static const bool v1 = [] { const char* e = getenv("KWS_FUSE_V1"); return e && e[0] == '1'; }();
   const bool transposed = !v1 && p.c0 == TILE_M;
   KWS_T0(h, KC_CONV1, st);
-  if (transposed) conv1_block1_kernel<true><<<grid, FUSE_THREADS, lay.total, st>>>(p);
-  else conv1_block1_kernel<false><<<grid, FUSE_THREADS, lay.total, st>>>(p);
+  if (transposed) conv1_block1_kernel<true><<<grid, FuseRoles<true>::THREADS, lay.total, st>>>(p);
+  else conv1_block1_kernel<false><<<grid, FuseRoles<false>::THREADS, lay.total, st>>>(p);
   KWS_T1(h, st);
   if (debug_sync() && cudaDeviceSynchronize() != cudaSuccess)
     return fail(h, KWS_ECUDA, std::string("conv1_block1_kernel: ") + cudaGetErrorString(cudaGetLastError()));
