@@ -147,6 +147,8 @@ void kws_destroy(kws_t* h) {
     if (h->pin_in[i]) cudaFreeHost(h->pin_in[i]);
     if (h->pin_out[i]) cudaFreeHost(h->pin_out[i]);
   }
+  if (h->stretch_ws) cudaFree(h->stretch_ws);
+  if (h->stretch_stage) cudaFree(h->stretch_stage);
   if (h->copy_pool) copy_pool_destroy(h->copy_pool);
   if (h->ev_user) cudaEventDestroy(h->ev_user);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -244,6 +246,38 @@ int kws_augment_pcm16(kws_t* h, const int16_t* pcm, float divisor, const int32_t
                       const float* fg_vol, float* out, int B, int clamp, void* stream) {
   if (h && !(divisor > 0.0f)) return fail(h, KWS_EINVAL, "divisor must be positive");
   return augment_common(h, nullptr, pcm, divisor, shift, bg_file, bg_off, bg_vol, fg_vol, out, B, clamp, stream);
+}
+
+int kws_time_stretch_pcm16(kws_t* h, const int16_t* pcm, int B, float rate, int16_t* out, void* stream) {
+  if (!h) return KWS_EINVAL;
+  if (B < 0) return fail(h, KWS_EINVAL, "negative batch");
+  if (B == 0) return KWS_OK;
+  if (!pcm || !out) return fail(h, KWS_EINVAL, "null pointer");
+  return launch_time_stretch(h, pcm, B, rate, 32767.0f, out, static_cast<cudaStream_t>(stream));
+}
+
+int kws_time_stretch_host_pcm16(kws_t* h, const int16_t* pcm_h, int B, float rate, int16_t* out_h) {
+  if (!h) return KWS_EINVAL;
+  if (B < 0) return fail(h, KWS_EINVAL, "negative batch");
+  if (B == 0) return KWS_OK;
+  if (!pcm_h || !out_h) return fail(h, KWS_EINVAL, "null pointer");
+  KWS_CUDA(h, cudaSetDevice(h->device));
+  const int chunk = std::min(B, 8192);
+  const size_t clip_bytes = static_cast<size_t>(L) * sizeof(int16_t);
+  int rc = ensure_bytes(h, &h->stretch_stage, &h->stretch_stage_bytes, 2 * chunk * clip_bytes);
+  if (rc) return rc;
+  int16_t* d_in = static_cast<int16_t*>(h->stretch_stage);
+  int16_t* d_out = d_in + static_cast<size_t>(chunk) * L;
+  cudaStream_t st = h->own_stream;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nb = std::min(chunk, B - b0);
+    KWS_CUDA(h, cudaMemcpyAsync(d_in, pcm_h + static_cast<size_t>(b0) * L, nb * clip_bytes, cudaMemcpyHostToDevice, st));
+    rc = launch_time_stretch(h, d_in, nb, rate, 32767.0f, d_out, st);
+    if (rc) { cudaStreamSynchronize(st); return rc; }
+    KWS_CUDA(h, cudaMemcpyAsync(out_h + static_cast<size_t>(b0) * L, d_out, nb * clip_bytes, cudaMemcpyDeviceToHost, st));
+    KWS_CUDA(h, cudaStreamSynchronize(st));
+  }
+  return KWS_OK;
 }
 
 int kws_frontend_config(kws_t* h, int win, int hop, int n_mel, int n_keep, float f_lo, float f_hi, int sample_rate) {

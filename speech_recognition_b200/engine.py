@@ -157,6 +157,24 @@ class Engine:
                                              self._dp(out_t), B, int(clamp), self._stream()))
         return out_t
 
+    # -- speed-TTA view --
+    def time_stretch(self, pcm_t, rate=0.9, out_t=None):
+        """create_tta_set.py:16-22 on the device: int16 PCM [B,16000] -> int16 PCM of the slowed clips."""
+        import torch
+        B = pcm_t.shape[0]
+        self._dev(pcm_t, torch.int16, (B, SAMPLES), "pcm")
+        if out_t is None:
+            out_t = torch.empty((B, SAMPLES), dtype=torch.int16, device=pcm_t.device)
+        self._dev(out_t, torch.int16, (B, SAMPLES), "out")
+        self._check(self.lib.kws_time_stretch_pcm16(self.h, self._dp(pcm_t), B, float(rate), self._dp(out_t), self._stream()))
+        return out_t
+
+    def time_stretch_host(self, pcm, rate=0.9, out=None):
+        pcm = _in(pcm, np.int16, (len(pcm), SAMPLES), "pcm")
+        out = _out(out, np.int16, pcm.shape, "out")
+        self._check(self.lib.kws_time_stretch_host_pcm16(self.h, _hp(pcm), pcm.shape[0], float(rate), _hp(out)))
+        return out
+
     # -- stage 1b --
     def frontend_config(self, window_size_samples=480, window_stride_samples=160, n_mel=40, n_keep=None,
                         lower_edge_hertz=80.0, upper_edge_hertz=7600.0, sample_rate=16000):

@@ -40,16 +40,29 @@ class Model:
         """(probs + loud_probs + left_probs) / 3 and argmax (make_submission.py:120-146)."""
         return self.engine.predict_host(x, views=views, slot=self.slot)
 
-    def predict_speed_tta(self, x, x_slow):
+    def predict_speed_tta(self, x, x_slow=None, tta_speed=0.9):
         """make_submission.py:124-146 with ``use_speed_tta``: x_slow holds the time-stretched copies that
         create_tta_set.py wrote (librosa, offline).  Views: x, roll(x, -1500), 1.2 x, x_slow,
         clip(1.1 x_slow, -1, 1), 0.9 x_slow; the reference divides the SIX probability vectors by 10
-        (sic, :140) -- kept, it does not change the argmax.  Returns (probs f32 [N,C], argmax int32 [N])."""
+        (sic, :140) -- kept, it does not change the argmax.  Returns (probs f32 [N,C], argmax int32 [N]).
+
+        With ``x_slow=None`` the slowed set is produced here, on the device, the way create_tta_set.py:16-22 produces
+        its WAV files: ``x`` must then be the clips' int16 PCM; both sets are decoded like the reference's DecodeWav
+        (/ 32768, input_data.py:334-336)."""
         import torch
         eng = self.engine
         dev = f"cuda:{eng.device}"
-        xt = torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(dev)
-        st = torch.from_numpy(np.ascontiguousarray(x_slow, np.float32)).to(dev)
+        if x_slow is None:
+            x = np.asarray(x)
+            if x.dtype != np.int16:
+                raise ValueError("predict_speed_tta without x_slow needs the int16 PCM of the clips")
+            pcm = torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+            slow = eng.time_stretch(pcm, tta_speed)
+            xt = pcm.to(torch.float32) * (1.0 / 32768.0)
+            st = slow.to(torch.float32) * (1.0 / 32768.0)
+        else:
+            xt = torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(dev)
+            st = torch.from_numpy(np.ascontiguousarray(x_slow, np.float32)).to(dev)
         n = xt.shape[0]
         p_a, _ = eng.forward(xt, views=TTA_SHIPPED, slot=self.slot)                 # mean of 3
         p_b, _ = eng.forward(st, views=((0, 1.0), (0, 0.9)), slot=self.slot)        # mean of 2

@@ -10,7 +10,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import h5_writer  # noqa: E402
-from oracle import augment, frontend, network, driver  # noqa: E402
+from oracle import augment, frontend, network, driver, stretch  # noqa: E402
 from speech_recognition_b200 import (AudioProcessor, Engine, load_model, prepare_model_settings, synth,  # noqa: E402
                                      submission, pseudo, TTA_SHIPPED, TTA_8)
 from speech_recognition_b200.audio_processor import draw_augmentation_params  # noqa: E402
@@ -243,3 +243,46 @@ def test_submission_and_pseudo_surface(tmp_path, engine):
     assert np.array_equal(voted, r_voted) and np.array_equal(clear, r_clear)
     assert np.array_equal(pseudo.unanimity(engine, three[0], three[1], three[2]),
                           (three[0] == three[1]) & (three[0] == three[2]))
+
+
+def test_time_stretch_against_oracle(engine):
+    """Speed-TTA view (create_tta_set.py:10-22): the phase-vocoder kernel against the restatement of librosa's published
+    algorithm on int16 PCM in / int16 PCM out.  Transcendentals (atan2f / sincosf / hypotf) and the FFT summation order
+    differ from NumPy's by rounding, and np.int16(x * 32767) truncates: a sample may land on the other side of an
+    integer, never further -- |delta| <= 1 LSB, and only on a small fraction of the samples."""
+    _, pcm = synth.make_clips(6, seed=321, return_pcm=True)
+    pcm[0, :] = 0                                                     # digital silence
+    pcm[1] = np.int16(np.round(8000 * np.sin(2 * np.pi * 1000.0 * np.arange(16000) / 16000.0)))
+    ref = stretch.create_tta_batch(pcm, 0.9)
+    got = engine.time_stretch(torch.from_numpy(pcm).cuda(), 0.9).cpu().numpy()
+    assert got.dtype == np.int16 and got.shape == (6, 16000)
+    assert np.array_equal(got[0], ref[0]) and not got[0].any()
+    d = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+    assert d.max() <= 1, (d.max(), np.unravel_index(d.argmax(), d.shape))
+    assert (d > 0).mean() < 0.02, (d > 0).mean()
+    assert np.abs(ref[1:]).max() > 1000                               # the comparison is not between silences
+    host = engine.time_stretch_host(pcm, 0.9)
+    assert np.array_equal(host, got)
+    # other rates take the same path (output = the last 16000 samples of a longer clip)
+    got75 = engine.time_stretch(torch.from_numpy(pcm[2:4]).cuda(), 0.75).cpu().numpy()
+    ref75 = stretch.create_tta_batch(pcm[2:4], 0.75)
+    assert np.abs(got75.astype(np.int32) - ref75.astype(np.int32)).max() <= 1
+    with pytest.raises(Exception, match="rate"):
+        engine.time_stretch(torch.from_numpy(pcm[:1]).cuda(), 1.5)
+
+
+def test_speed_tta_end_to_end(engine):
+    """make_submission.py:124-146 with use_speed_tta, the slowed set produced on the device: six views / 10 against the
+    oracle (time stretch + driver arithmetic + float64 network) on a trained checkpoint."""
+    from speech_recognition_b200 import Model
+    engine.set_precision("fp32")
+    w = synth.trained_weights(195)
+    m = Model(195, w, engine=engine, slot=1)
+    x, lab = synth.make_word_clips(12, 12, seed=99, return_labels=True)
+    pcm = np.int16(np.round(x.numpy() * 32768.0))
+    probs, amax = m.predict_speed_tta(pcm)
+    xf = pcm.astype(np.float32) / np.float32(32768.0)
+    slow = stretch.create_tta_batch(pcm, 0.9).astype(np.float32) / np.float32(32768.0)
+    r_probs, r_amax = driver.speed_tta_predict(lambda v: network.forward(v, w, 195, dtype=torch.float64), xf, slow)
+    assert np.abs(probs - r_probs).max() < 2e-3                       # +-1 LSB differences of the slowed PCM reach the softmax
+    assert np.array_equal(amax, r_amax)
