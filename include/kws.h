@@ -110,8 +110,8 @@ int kws_augment_pcm16(kws_t* h, const int16_t* pcm, float divisor, const int32_t
  * (periodic Hann, centered, reflect-padded) -> phase vocoder -> ISTFT, the last 16000 samples, 16-bit PCM in and out
  * [B,16000] (the reference reads and writes WAV files here).  0 < rate <= 1 (the reference uses 0.9).  librosa is not
  * vendored by the reference: the algorithm is the published librosa 0.5.x one (parity unpinned, oracle/stretch.py). */
-int kws_time_stretch_pcm16(kws_t* h, const int16_t* pcm, int B, float rate, int16_t* out, void* stream);
-int kws_time_stretch_host_pcm16(kws_t* h, const int16_t* pcm_h, int B, float rate, int16_t* out_h);
+int kws_time_stretch_pcm16(kws_t* h, const int16_t* pcm, int B, double rate, int16_t* out, void* stream);
+int kws_time_stretch_host_pcm16(kws_t* h, const int16_t* pcm_h, int B, double rate, int16_t* out_h);
 
 /* ---- stage 1b: STFT -> |.| -> mel -> log -> DCT  (input_data.py:361-381) ---- */
 /* model_settings keys of prepare_model_settings (model.py:1785-1829): window /

@@ -37,8 +37,8 @@ SIGNATURES = {
     "kws_set_noise_bank": (_i, [_vp, _vp, C.POINTER(_i64), _i]),
     "kws_augment": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "kws_augment_pcm16": (_i, [_vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
-    "kws_time_stretch_pcm16": (_i, [_vp, _vp, _i, _f, _vp, _vp]),
-    "kws_time_stretch_host_pcm16": (_i, [_vp, _vp, _i, _f, _vp]),
+    "kws_time_stretch_pcm16": (_i, [_vp, _vp, _i, _d, _vp, _vp]),
+    "kws_time_stretch_host_pcm16": (_i, [_vp, _vp, _i, _d, _vp]),
     "kws_frontend_config": (_i, [_vp, _i, _i, _i, _i, _f, _f, _i]),
     "kws_frontend_config_contrib": (_i, [_vp, _i, _i, _i, _f, _f, _i, _i]),
     "kws_frontend_frames": (_i, [_vp]),

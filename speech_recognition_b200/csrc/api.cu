@@ -248,7 +248,7 @@ int kws_augment_pcm16(kws_t* h, const int16_t* pcm, float divisor, const int32_t
   return augment_common(h, nullptr, pcm, divisor, shift, bg_file, bg_off, bg_vol, fg_vol, out, B, clamp, stream);
 }
 
-int kws_time_stretch_pcm16(kws_t* h, const int16_t* pcm, int B, float rate, int16_t* out, void* stream) {
+int kws_time_stretch_pcm16(kws_t* h, const int16_t* pcm, int B, double rate, int16_t* out, void* stream) {
   if (!h) return KWS_EINVAL;
   if (B < 0) return fail(h, KWS_EINVAL, "negative batch");
   if (B == 0) return KWS_OK;
@@ -256,7 +256,7 @@ int kws_time_stretch_pcm16(kws_t* h, const int16_t* pcm, int B, float rate, int1
   return launch_time_stretch(h, pcm, B, rate, 32767.0f, out, static_cast<cudaStream_t>(stream));
 }
 
-int kws_time_stretch_host_pcm16(kws_t* h, const int16_t* pcm_h, int B, float rate, int16_t* out_h) {
+int kws_time_stretch_host_pcm16(kws_t* h, const int16_t* pcm_h, int B, double rate, int16_t* out_h) {
   if (!h) return KWS_EINVAL;
   if (B < 0) return fail(h, KWS_EINVAL, "negative batch");
   if (B == 0) return KWS_OK;

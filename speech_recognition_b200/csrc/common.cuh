@@ -108,7 +108,7 @@ struct kws_handle {
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   // speed-TTA time stretch (stretch.cu): tables of the last rate + per-CTA STFT scratch, host-entry staging
-  void* stretch_ws = nullptr; float stretch_rate = 0.0f; int stretch_n_out = 0; bool stretch_attr_done = false;
+  void* stretch_ws = nullptr; double stretch_rate = 0.0; int stretch_n_out = 0; bool stretch_attr_done = false;
   void* stretch_stage = nullptr; size_t stretch_stage_bytes = 0;
   // cuTensorMapEncodeTiled results keyed by (buffer, shape, box): the activation buffers and chunk sizes repeat from
   // call to call, so every launch after the first of a shape finds its tensor maps here (tc_net.cu)
@@ -169,7 +169,7 @@ int launch_augment(kws_handle* h, const float* wav, const int16_t* pcm, float pc
                    const int32_t* shift, const int32_t* bg_file, const int32_t* bg_off,
                    const float* bg_vol, const float* fg_vol, float* out, int B, int clamp,
                    cudaStream_t st);
-int launch_time_stretch(kws_handle* h, const int16_t* pcm, int B, float rate, float divisor, int16_t* out, cudaStream_t st);
+int launch_time_stretch(kws_handle* h, const int16_t* pcm, int B, double rate, float divisor, int16_t* out, cudaStream_t st);
 int frontend_build(kws_handle* h, int win, int hop, int n_mel, int n_keep, float f_lo, float f_hi,
                    int sample_rate, int flavour = 0);
 int launch_features_f32(kws_handle* h, const float* wav, int B, int kind, float* out, cudaStream_t st);

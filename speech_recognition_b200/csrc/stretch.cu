@@ -187,13 +187,13 @@ __global__ void __launch_bounds__(ST_THREADS, 2) time_stretch_kernel(const Stret
 
 }  // namespace
 
-int launch_time_stretch(kws_handle* h, const int16_t* pcm, int B, float rate, float divisor, int16_t* out, cudaStream_t st) {
+int launch_time_stretch(kws_handle* h, const int16_t* pcm, int B, double rate, float divisor, int16_t* out, cudaStream_t st) {
   if (B == 0) return KWS_OK;
-  if (!(rate > 0.0f) || rate > 1.0f) return fail(h, KWS_EUNSUPPORTED, "time stretch supports 0 < rate <= 1 (create_tta_set.py uses 0.9)");
+  if (!(rate > 0.0) || rate > 1.0) return fail(h, KWS_EUNSUPPORTED, "time stretch supports 0 < rate <= 1 (create_tta_set.py uses 0.9)");
   // time steps exactly as np.arange(0, n_frames, rate, dtype=float64): start + i * step
   std::vector<double> steps;
   {
-    const double r = static_cast<double>(rate);
+    const double r = rate;                                        // a double, like the Python float the reference passes: float(0.9) * 10 < 9
     const int n = static_cast<int>(std::ceil(static_cast<double>(ST_FRAMES_IN) / r));
     for (int i = 0; i < n; ++i) steps.push_back(i * r);
   }
@@ -233,10 +233,10 @@ int launch_time_stretch(kws_handle* h, const int16_t* pcm, int B, float rate, fl
   p.pcm = pcm; p.out = out; p.B = B; p.divisor = divisor; p.n_out = n_out;
   const size_t smem = ST_N * sizeof(double2) + static_cast<size_t>(ola_len) * sizeof(float);
   if (!h->stretch_attr_done) {
-    KWS_CUDA(h, cudaFuncSetAttribute(time_stretch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-    h->stretch_attr_done = true;
+    KWS_CUDA(h, cudaFuncSetAttribute(time_stretch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    h->stretch_attr_done = true;                                  // (two CTAs per SM up to 113 KB: rates >= 0.89)
   }
-  if (smem > 113 * 1024) return fail(h, KWS_EUNSUPPORTED, "time stretch rate too small for the overlap-add buffer");
+  if (smem > 160 * 1024) return fail(h, KWS_EUNSUPPORTED, "time stretch rate too small for the overlap-add buffer");
   KWS_T0(h, KC_OTHER, st);
   time_stretch_kernel<<<grid, ST_THREADS, smem, st>>>(p);
   KWS_T1(h, st);

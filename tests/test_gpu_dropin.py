@@ -252,7 +252,13 @@ def test_time_stretch_against_oracle(engine):
     integer, never further -- |delta| <= 1 LSB, and only on a small fraction of the samples."""
     _, pcm = synth.make_clips(6, seed=321, return_pcm=True)
     pcm[0, :] = 0                                                     # digital silence
-    pcm[1] = np.int16(np.round(8000 * np.sin(2 * np.pi * 1000.0 * np.arange(16000) / 16000.0)))
+    # a loud tone over a +-20 LSB noise floor.  (Without the floor -- a bin-centred tone whose other bins are EXACTLY zero
+    # until the reflect-padded last frames -- the phase accumulators of those bins integrate the angles of rounding
+    # noise for 30 frames, and the output of the last 2000 samples depends on the FFT's summation order: NumPy's
+    # direct transform and a two-real-frames-per-complex-transform one already differ by thousands of LSB there.
+    # That is a property of the plain phase vocoder, librosa's included, not of an implementation.)
+    rs = np.random.RandomState(5)
+    pcm[1] = np.int16(np.round(8000 * np.sin(2 * np.pi * 1000.0 * np.arange(16000) / 16000.0) + rs.normal(0, 20, 16000)))
     ref = stretch.create_tta_batch(pcm, 0.9)
     got = engine.time_stretch(torch.from_numpy(pcm).cuda(), 0.9).cpu().numpy()
     assert got.dtype == np.int16 and got.shape == (6, 16000)
