@@ -54,6 +54,9 @@ extern "C" {
 
 #define KWS_ARCH_195 195      /* model.py:775-838 (also exp 206)                  */
 #define KWS_ARCH_106 106      /* 32-class variant from the logs_106 graph         */
+#define KWS_ARCH_TIME_SLICED 716   /* conv_1d_time_sliced_model(filter_mult=1), model.py:716-772: conv1d_1 with 32
+                                      filters, 13 depthwise-separable blocks, GlobalAveragePooling1D -> Dense(256)
+                                      -> ReLU6 -> Dense(num_classes) head; num_classes = dense_2/kernel.shape[1] */
 
 typedef struct kws_handle kws_t;
 

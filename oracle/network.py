@@ -37,6 +37,10 @@ ARCHS = {
               dense1_bias=False, pool="attn_mean", classes=32),
 }
 ARCHS[206] = ARCHS[195]
+# conv_1d_time_sliced_model(filter_mult=1), model.py:716-772
+ARCHS[716] = dict(conv1=32, blocks=[(64, 1), (128, 2), (128, 1), (192, 2), (192, 1), (256, 2), (256, 1), (320, 2),
+                                    (320, 1), (384, 2), (384, 1), (512, 2), (512, 1)],
+                  dense1_bias=False, pool="gap_dense", hidden=256, classes=12)
 
 
 def same_pad(T: int, k: int, s: int):
@@ -75,6 +79,10 @@ def weight_shapes(arch: int):
         shapes[f"conv1d_{i + 1}/kernel"] = (1, c, co)
         bn(i + 1, co)
         c = co
+    if a["pool"] == "gap_dense":
+        shapes["dense_1/kernel"] = (c, a["hidden"])
+        shapes["dense_2/kernel"] = (a["hidden"], a["classes"])
+        return shapes
     T_last = layer_lengths(arch)[-1]
     shapes["dense_1/kernel"] = (T_last * c, T_last)
     if a["dense1_bias"]:
@@ -131,6 +139,13 @@ def forward(x, w, arch: int = 195, dtype=torch.float32, return_activations: bool
     xt = y.transpose(1, 2).contiguous()                        # [B,T,C] channels-last
     B, T, C = xt.shape
     d1 = torch.as_tensor(w["dense_1/kernel"], dtype=dtype)
+    if a["pool"] == "gap_dense":                                # model.py:759-765
+        z = torch.clamp(xt.mean(dim=1) @ d1, 0.0, 6.0)         # GlobalAveragePooling1D -> Dense(256, no bias) -> relu6
+        logits = z @ torch.as_tensor(w["dense_2/kernel"], dtype=dtype)
+        probs = torch.softmax(logits, dim=-1)
+        if return_activations:
+            return probs.numpy(), logits.numpy(), [t.transpose(1, 2).contiguous().numpy() for t in acts]
+        return probs.numpy()
     att = xt.reshape(B, T * C) @ d1                            # flatten index t*C+c
     if a["dense1_bias"]:
         att = att + torch.as_tensor(w["dense_1/bias"], dtype=dtype)

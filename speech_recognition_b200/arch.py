@@ -21,6 +21,13 @@ ARCHS = {
               dense1_bias=False, pool="attn_mean", classes=32),
 }
 ARCHS[206] = ARCHS[195]
+# conv_1d_time_sliced_model(filter_mult=1) (reference model.py:716-772): conv1d_1 with 32 filters, 13 blocks, head =
+# GlobalAveragePooling1D -> Dense(256, no bias) -> ReLU6 -> Dense(num_classes, softmax, no bias).  No checkpoint of it is
+# shipped; num_classes is an argument of the builder (12 here, the competition's label set).
+TIME_SLICED = 716
+ARCHS[TIME_SLICED] = dict(conv1=32, blocks=[(64, 1), (128, 2), (128, 1), (192, 2), (192, 1), (256, 2), (256, 1), (320, 2),
+                                            (320, 1), (384, 2), (384, 1), (512, 2), (512, 1)],
+                          dense1_bias=False, pool="gap_dense", hidden=256, classes=12)
 
 
 def same_pad(T: int, k: int, s: int):
@@ -31,7 +38,7 @@ def same_pad(T: int, k: int, s: int):
 
 
 def layer_lengths(arch: int, input_size: int = INPUT_SAMPLES):
-    """[n_patches, T after conv1d_1, T after each of the 11 blocks]."""
+    """[n_patches, T after conv1d_1, T after each block]."""
     n_patch, _, _ = same_pad(input_size, PATCH, PATCH_STRIDE)
     T = (n_patch - 3) // 2 + 1
     out = [n_patch, T]
@@ -56,6 +63,10 @@ def weight_shapes(arch: int):
         shapes[f"conv1d_{i + 1}/kernel"] = (1, c, co)
         bn(i + 1, co)
         c = co
+    if a["pool"] == "gap_dense":
+        shapes["dense_1/kernel"] = (c, a["hidden"])
+        shapes["dense_2/kernel"] = (a["hidden"], a["classes"])
+        return shapes
     T_last = layer_lengths(arch)[-1]
     shapes["dense_1/kernel"] = (T_last * c, T_last)
     if a["dense1_bias"]:

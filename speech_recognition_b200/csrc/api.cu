@@ -135,6 +135,7 @@ void kws_destroy(kws_t* h) {
   for (int i = 0; i < KWS_MAX_MODELS; ++i) {
     if (h->models[i].blob) cudaFree(h->models[i].blob);
     if (h->models[i].tc_blob) cudaFree(h->models[i].tc_blob);
+    if (h->models[i].hidden_ws) cudaFree(h->models[i].hidden_ws);
   }
   if (h->fe.blob) cudaFree(h->fe.blob);
   if (h->fe.tc_blob) cudaFree(h->fe.tc_blob);
@@ -331,7 +332,7 @@ int kws_debug_activation(kws_t* h, int slot, const float* wav, int B, const int3
   int rc = make_views(h, view_shift_h, view_gain_h, n_views, &vt);
   if (rc) return rc;
   if (slot < 0 || slot >= KWS_MAX_MODELS || !h->models[slot].loaded) return fail(h, KWS_ESTATE, "model not loaded");
-  if (layer < 0 || layer > NUM_BLOCKS || !out || !wav || B <= 0) return fail(h, KWS_EINVAL, "bad arguments");
+  if (layer < 0 || layer > h->models[slot].n_blocks || !out || !wav || B <= 0) return fail(h, KWS_EINVAL, "bad arguments");
   if (B * n_views > h->max_rows) return fail(h, KWS_EINVAL, "debug activation needs B*n_views <= max_rows");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   rc = h->precision == KWS_PREC_FP32

@@ -12,7 +12,8 @@
 namespace kws {
 
 constexpr int L = KWS_SAMPLES;           // samples per clip
-constexpr int NUM_BLOCKS = 11;           // depthwise-separable blocks after conv1d_1
+constexpr int MAX_BLOCKS = 13;           // depthwise-separable blocks after conv1d_1: 11 (exp 195 / 206 / 106) or 13 (conv_1d_time_sliced)
+constexpr int TIMED_BLOCKS = 11;         // blocks with their own kws_timing_read slot
 constexpr int NUM_SMS_B200 = 148;
 
 struct ViewTable {                        // TTA views, passed to kernels by value
@@ -29,22 +30,30 @@ struct Model {
   bool loaded = false;
   int arch = 0, classes = 0, c0 = 0, t0 = 0, t_last = 0, c_last = 0;
   bool dense1_bias = false, pool_max_avg = false;
-  LayerDesc layers[NUM_BLOCKS];
+  int n_blocks = 0;
+  // head_kind 0: attention pooling head (model.py:819-830; exp 106: attention-weighted mean);
+  //           1: GlobalAveragePooling1D -> Dense(hidden, no bias) -> ReLU6 -> Dense(classes, softmax)  (model.py:759-765)
+  int head_kind = 0, hidden = 0;
+  int c0_tc = 0;                          // conv1d_1 width of the tensor-core images: c0 rounded up to 64 (zero filters)
+  LayerDesc layers[MAX_BLOCKS];
   // fp32 device weights (Keras layouts), all inside one allocation `blob`
   float* blob = nullptr;
   float* w_conv1 = nullptr;               // [120, c0]
-  float* bn_scale[NUM_BLOCKS + 1];        // s = rsqrt(var+eps)*gamma
-  float* bn_shift[NUM_BLOCKS + 1];        // beta - mean*s
-  float* w_dw[NUM_BLOCKS];                // [3, cin]
-  float* w_pw[NUM_BLOCKS];                // [cin, cout]
-  float* w_d1 = nullptr;                  // [t_last*c_last, t_last]
+  float* bn_scale[MAX_BLOCKS + 1];        // s = rsqrt(var+eps)*gamma
+  float* bn_shift[MAX_BLOCKS + 1];        // beta - mean*s
+  float* w_dw[MAX_BLOCKS];                // [3, cin]
+  float* w_pw[MAX_BLOCKS];                // [cin, cout]
+  float* tc_shift0 = nullptr;             // conv1d_1 BN shift padded to c0_tc (== bn_shift[0] when c0 is a multiple of 64)
+  float* hidden_ws = nullptr;             // head_kind 1: [max rows][hidden] activations of the hidden Dense layer
+  size_t hidden_ws_rows = 0;
+  float* w_d1 = nullptr;                  // [t_last*c_last, t_last]  (head_kind 1: [c_last, hidden])
   float* b_d1 = nullptr;                  // [t_last] (zeros when the arch has no bias)
   float* w_d2 = nullptr;                  // [feat, classes]
   // tensor-core operand images (fp16, pre-swizzled UMMA K-major SW128 slabs)
   void* tc_blob = nullptr;
   __half* tc_conv1 = nullptr;             // [2 slabs][c0 rows][64] swizzled, 80 folded taps
-  __half* tc_pw[NUM_BLOCKS];              // [cin/64 slabs][cout rows][64] swizzled, BN scale folded in
-  __half* tc_dw[NUM_BLOCKS];              // depthwise taps [3][cin] fp16
+  __half* tc_pw[MAX_BLOCKS];              // [cin/64 slabs][cout rows][64] swizzled, BN scale folded in
+  __half* tc_dw[MAX_BLOCKS];              // depthwise taps [3][cin] fp16
   size_t max_act_elems = 0;               // max over layers of T*C (per clip-view)
 };
 

@@ -9,6 +9,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "gemm_f32.cuh"
 
 namespace kws {
 
@@ -254,6 +255,91 @@ __global__ void to_float_kernel(const T* __restrict__ src, float* __restrict__ d
 }
 }  // namespace
 
+// ---- head of conv_1d_time_sliced_model (model.py:759-765) ----
+// GlobalAveragePooling1D as the A-operand loader of the hidden Dense layer's GEMM: A[row, c] = mean_t x[row, t, c]
+template <typename TAct>
+struct LoadGap {
+  const TAct* x; int T, C;
+  __device__ __forceinline__ float operator()(int m, int c) const {
+    const TAct* base = x + static_cast<size_t>(m) * T * C + c;
+    float s = 0.0f;
+    for (int t = 0; t < T; ++t) s += to_float(base[static_cast<size_t>(t) * C]);
+    return __fdiv_rn(s, static_cast<float>(T));
+  }
+};
+struct EpiRelu6 {            // Dense(256, use_bias=False) -> Activation(relu6)
+  float* C;
+  __device__ __forceinline__ void operator()(int m, int n, float (&acc)[G_TM][G_TN], int M, int N) const {
+#pragma unroll
+    for (int i = 0; i < G_TM; ++i)
+#pragma unroll
+      for (int j = 0; j < G_TN; ++j)
+        if (m + i < M && n + j < N) C[static_cast<size_t>(m + i) * N + n + j] = fminf(fmaxf(acc[i][j], 0.0f), 6.0f);
+  }
+};
+
+namespace {
+// Dense(classes, softmax, no bias) per view, TTA mean in view order, first-index argmax: one warp per clip
+__global__ void __launch_bounds__(256) dense_softmax_tta_kernel(const float* __restrict__ hid, int hidden, int n_views, int n_clips,
+                                                                const float* __restrict__ w2, int classes,
+                                                                float* __restrict__ probs_mean, int32_t* __restrict__ argmax) {
+  extern __shared__ float s_w2[];                         // [hidden][classes]
+  for (int i = threadIdx.x; i < hidden * classes; i += blockDim.x) s_w2[i] = __ldg(&w2[i]);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  for (int b = blockIdx.x * wpb + warp; b < n_clips; b += gridDim.x * wpb) {
+    float acc_p = 0.0f;
+    for (int v = 0; v < n_views; ++v) {
+      const float* x = hid + (static_cast<size_t>(b) * n_views + v) * hidden;
+      float l = -INFINITY;
+      if (lane < classes) {
+        float d = 0.0f;
+        for (int k = 0; k < hidden; ++k) d = fmaf(__ldg(&x[k]), s_w2[k * classes + lane], d);
+        l = d;
+      }
+      const float mx = warp_max(l);
+      const float e = lane < classes ? expf(l - mx) : 0.0f;
+      const float s = warp_sum(e);
+      acc_p = __fadd_rn(acc_p, __fdiv_rn(e, s));
+    }
+    const float pm = __fdiv_rn(acc_p, static_cast<float>(n_views));
+    if (probs_mean && lane < classes) probs_mean[static_cast<size_t>(b) * classes + lane] = pm;
+    float best = lane < classes ? pm : -INFINITY;
+    int idx = lane < classes ? lane : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+    }
+    if (argmax && lane == 0) argmax[b] = idx;
+  }
+}
+}  // namespace
+
+static int launch_head_gap_dense(kws_handle* h, Model& m, const void* act, bool act_half, int n_clips, int n_views,
+                                 float* probs_mean, int32_t* argmax, cudaStream_t st) {
+  const int rows = n_clips * n_views;
+  if (m.hidden_ws_rows < static_cast<size_t>(rows)) {
+    if (m.hidden_ws) { KWS_CUDA(h, cudaStreamSynchronize(st)); cudaFree(m.hidden_ws); m.hidden_ws = nullptr; }
+    KWS_CUDA(h, cudaMalloc(&m.hidden_ws, static_cast<size_t>(rows) * m.hidden * sizeof(float)));
+    m.hidden_ws_rows = rows;
+  }
+  EpiRelu6 e{m.hidden_ws};
+  KWS_T0(h, KC_HEAD, st);
+  if (act_half) launch_gemm_f32(LoadGap<__half>{static_cast<const __half*>(act), m.t_last, m.c_last}, m.w_d1, rows, m.hidden, m.c_last, e, st);
+  else launch_gemm_f32(LoadGap<float>{static_cast<const float*>(act), m.t_last, m.c_last}, m.w_d1, rows, m.hidden, m.c_last, e, st);
+  KWS_T1(h, st);
+  KWS_LAUNCH_CHECK(h);
+  const int grid = std::max(1, std::min(4 * h->num_sms, (n_clips + 7) / 8));
+  KWS_T0(h, KC_HEAD, st);
+  dense_softmax_tta_kernel<<<grid, 256, static_cast<size_t>(m.hidden) * m.classes * sizeof(float), st>>>(
+      m.hidden_ws, m.hidden, n_views, n_clips, m.w_d2, m.classes, probs_mean, argmax);
+  KWS_T1(h, st);
+  KWS_LAUNCH_CHECK(h);
+  return KWS_OK;
+}
+
 int launch_to_float(kws_handle* h, const void* src, bool src_half, float* dst, size_t n, cudaStream_t st) {
   if (n == 0) return KWS_OK;
   const int grid = static_cast<int>(std::min<size_t>((n + 255) / 256, 4096));
@@ -265,6 +351,9 @@ int launch_to_float(kws_handle* h, const void* src, bool src_half, float* dst, s
 
 int launch_head(kws_handle* h, Model& m, const void* act, bool act_half, int n_clips, int n_views,
                 float* probs_mean, int32_t* argmax, cudaStream_t st) {
+  if (m.classes > HEAD_MAX_CLASSES) return fail(h, KWS_EUNSUPPORTED, "too many classes");
+  if (n_views < 1 || n_views > HEAD_WARPS) return fail(h, KWS_EINVAL, "n_views must be in 1..16");
+  if (m.head_kind == 1) return launch_head_gap_dense(h, m, act, act_half, n_clips, n_views, probs_mean, argmax, st);
   if (m.t_last != HEAD_T) return fail(h, KWS_EUNSUPPORTED, "head expects 9 time steps");
   if (m.classes > HEAD_MAX_CLASSES) return fail(h, KWS_EUNSUPPORTED, "too many classes");
   if (n_views < 1 || n_views > HEAD_WARPS) return fail(h, KWS_EINVAL, "n_views must be in 1..16");

@@ -17,12 +17,17 @@ int model_build_tc(kws_handle* h, Model& m, const std::vector<std::vector<float>
 
 namespace {
 
-struct ArchSpec { int conv1; int blocks[NUM_BLOCKS][2]; bool bias; bool max_avg; int classes; };
+// classes == 0: taken from the shape of dense_2/kernel (conv_1d_time_sliced_model has a num_classes argument)
+struct ArchSpec { int conv1; int n_blocks; int blocks[MAX_BLOCKS][2]; bool bias; bool max_avg; int classes; int head_kind; int hidden; };
 
-const ArchSpec kArch195 = {128, {{128, 1}, {192, 2}, {192, 1}, {256, 2}, {256, 1}, {320, 2}, {320, 1},
-                                 {384, 2}, {384, 1}, {512, 2}, {512, 1}}, true, true, 12};
-const ArchSpec kArch106 = {64, {{128, 1}, {192, 2}, {192, 1}, {256, 2}, {256, 1}, {320, 2}, {320, 1},
-                                {384, 2}, {384, 1}, {448, 2}, {448, 1}}, false, false, 32};
+const ArchSpec kArch195 = {128, 11, {{128, 1}, {192, 2}, {192, 1}, {256, 2}, {256, 1}, {320, 2}, {320, 1},
+                                     {384, 2}, {384, 1}, {512, 2}, {512, 1}}, true, true, 12, 0, 0};
+const ArchSpec kArch106 = {64, 11, {{128, 1}, {192, 2}, {192, 1}, {256, 2}, {256, 1}, {320, 2}, {320, 1},
+                                    {384, 2}, {384, 1}, {448, 2}, {448, 1}}, false, false, 32, 0, 0};
+// conv_1d_time_sliced_model(filter_mult=1), model.py:716-772: conv1d_1 has 32 filters, 13 blocks, and the head is
+// GlobalAveragePooling1D -> Dense(256, no bias) -> ReLU6 -> Dense(num_classes, softmax, no bias)
+const ArchSpec kArchTimeSliced = {32, 13, {{64, 1}, {128, 2}, {128, 1}, {192, 2}, {192, 1}, {256, 2}, {256, 1}, {320, 2}, {320, 1},
+                                           {384, 2}, {384, 1}, {512, 2}, {512, 1}}, false, false, 0, 1, 256};
 
 void same_pad(int T, int k, int s, int* out, int* pad_left) {   // TF 'SAME'
   *out = (T + s - 1) / s;
@@ -38,8 +43,9 @@ int model_build(kws_handle* h, int slot, int arch, const kws_tensor_h* t, int n)
   const ArchSpec* spec = nullptr;
   if (arch == KWS_ARCH_195 || arch == 206) spec = &kArch195;
   else if (arch == KWS_ARCH_106) spec = &kArch106;
+  else if (arch == KWS_ARCH_TIME_SLICED) spec = &kArchTimeSliced;
   else return fail(h, KWS_EUNSUPPORTED, "unknown architecture " + std::to_string(arch) +
-                                            " (this path ships 195/206 and 106)");
+                                            " (this path ships 195 / 206, 106 and conv_1d_time_sliced)");
   std::map<std::string, const kws_tensor_h*> by_name;
   for (int i = 0; i < n; ++i) {
     if (!t[i].name || !t[i].data) return fail(h, KWS_EINVAL, "null tensor entry");
@@ -58,15 +64,24 @@ int model_build(kws_handle* h, int slot, int arch, const kws_tensor_h* t, int n)
   Model& m = h->models[slot];
   if (m.blob) { cudaFree(m.blob); m.blob = nullptr; }
   if (m.tc_blob) { cudaFree(m.tc_blob); m.tc_blob = nullptr; }
+  if (m.hidden_ws) { cudaFree(m.hidden_ws); m.hidden_ws = nullptr; }
   m = Model();
   m.arch = arch; m.classes = spec->classes; m.c0 = spec->conv1;
   m.dense1_bias = spec->bias; m.pool_max_avg = spec->max_avg;
+  m.n_blocks = spec->n_blocks; m.head_kind = spec->head_kind; m.hidden = spec->hidden;
+  m.c0_tc = (m.c0 + 63) / 64 * 64;
+  if (m.classes == 0) {
+    auto it = by_name.find("dense_2/kernel");
+    if (it == by_name.end() || m.hidden == 0 || it->second->numel % m.hidden || it->second->numel / m.hidden > 32)
+      return fail(h, KWS_EINVAL, "dense_2/kernel missing or not [hidden, classes <= 32]");
+    m.classes = static_cast<int>(it->second->numel / m.hidden);
+  }
   int n_patch, pl;
   same_pad(L, 40, 20, &n_patch, &pl);                      // 800 patches, pad (10,10)
   m.t0 = (n_patch - 3) / 2 + 1;                            // 399
   int T = m.t0, C = m.c0;
-  m.max_act_elems = static_cast<size_t>(T) * C;
-  for (int i = 0; i < NUM_BLOCKS; ++i) {
+  m.max_act_elems = static_cast<size_t>(T) * m.c0_tc;
+  for (int i = 0; i < m.n_blocks; ++i) {
     LayerDesc& d = m.layers[i];
     d.cin = C; d.cout = spec->blocks[i][0]; d.stride = spec->blocks[i][1]; d.t_in = T;
     if (d.stride == 1) { d.t_out = T - 2; d.pad_left = 0; }
@@ -75,7 +90,7 @@ int model_build(kws_handle* h, int slot, int arch, const kws_tensor_h* t, int n)
     m.max_act_elems = std::max(m.max_act_elems, static_cast<size_t>(T) * C);
   }
   m.t_last = T; m.c_last = C;
-  const int feat = m.pool_max_avg ? 2 * C : C;
+  const int feat = m.head_kind == 1 ? m.hidden : (m.pool_max_avg ? 2 * C : C);
 
   // ---- gather + fold on the host ----
   std::vector<float> host;
@@ -86,8 +101,8 @@ int model_build(kws_handle* h, int slot, int arch, const kws_tensor_h* t, int n)
   if ((rc = get("conv1d_1/kernel", 120LL * m.c0, &p))) return rc;
   std::vector<float> conv1_host(p, p + 120 * m.c0);
   size_t o_conv1 = push(p, 120 * m.c0); push_pad();
-  size_t o_scale[NUM_BLOCKS + 1], o_shift[NUM_BLOCKS + 1], o_dw[NUM_BLOCKS], o_pw[NUM_BLOCKS];
-  std::vector<std::vector<float>> scales(NUM_BLOCKS + 1), shifts(NUM_BLOCKS + 1);
+  size_t o_scale[MAX_BLOCKS + 1], o_shift[MAX_BLOCKS + 1], o_dw[MAX_BLOCKS], o_pw[MAX_BLOCKS];
+  std::vector<std::vector<float>> scales(MAX_BLOCKS + 1), shifts(MAX_BLOCKS + 1);
   auto fold_bn = [&](int idx, int ch) -> int {
     const float *g, *b, *mu, *var;
     const std::string base = "batch_normalization_" + std::to_string(idx + 1) + "/";
@@ -108,8 +123,8 @@ int model_build(kws_handle* h, int slot, int arch, const kws_tensor_h* t, int n)
     return KWS_OK;
   };
   if ((rc = fold_bn(0, m.c0))) return rc;
-  std::vector<std::vector<float>> pw_host(NUM_BLOCKS), dw_host(NUM_BLOCKS);
-  for (int i = 0; i < NUM_BLOCKS; ++i) {
+  std::vector<std::vector<float>> pw_host(m.n_blocks), dw_host(m.n_blocks);
+  for (int i = 0; i < m.n_blocks; ++i) {
     const LayerDesc& d = m.layers[i];
     if ((rc = get("depthwise_conv2d_" + std::to_string(i + 1) + "/depthwise_kernel", 3LL * d.cin, &p))) return rc;
     dw_host[i].assign(p, p + 3 * d.cin);
@@ -119,8 +134,9 @@ int model_build(kws_handle* h, int slot, int arch, const kws_tensor_h* t, int n)
     o_pw[i] = push(p, static_cast<size_t>(d.cin) * d.cout); push_pad();
     if ((rc = fold_bn(i + 1, d.cout))) return rc;
   }
-  if ((rc = get("dense_1/kernel", 1LL * m.t_last * m.c_last * m.t_last, &p))) return rc;
-  size_t o_d1 = push(p, static_cast<size_t>(m.t_last) * m.c_last * m.t_last); push_pad();
+  const size_t d1_numel = m.head_kind == 1 ? static_cast<size_t>(m.c_last) * m.hidden : static_cast<size_t>(m.t_last) * m.c_last * m.t_last;
+  if ((rc = get("dense_1/kernel", static_cast<int64_t>(d1_numel), &p))) return rc;
+  size_t o_d1 = push(p, d1_numel); push_pad();
   std::vector<float> bias(m.t_last, 0.f);
   if (m.dense1_bias) {
     if ((rc = get("dense_1/bias", m.t_last, &p))) return rc;
@@ -129,12 +145,16 @@ int model_build(kws_handle* h, int slot, int arch, const kws_tensor_h* t, int n)
   size_t o_b1 = push(bias.data(), m.t_last); push_pad();
   if ((rc = get("dense_2/kernel", 1LL * feat * m.classes, &p))) return rc;
   size_t o_d2 = push(p, static_cast<size_t>(feat) * m.classes); push_pad();
+  std::vector<float> shift0_tc(m.c0_tc, 0.0f);                  // padded filters: zero weights, zero shift -> ReLU6(0) = 0
+  std::copy(shifts[0].begin(), shifts[0].end(), shift0_tc.begin());
+  size_t o_shift0_tc = push(shift0_tc.data(), m.c0_tc); push_pad();
 
   KWS_CUDA(h, cudaMalloc(&m.blob, host.size() * sizeof(float)));
   KWS_CUDA(h, cudaMemcpy(m.blob, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
   m.w_conv1 = m.blob + o_conv1;
-  for (int i = 0; i <= NUM_BLOCKS; ++i) { m.bn_scale[i] = m.blob + o_scale[i]; m.bn_shift[i] = m.blob + o_shift[i]; }
-  for (int i = 0; i < NUM_BLOCKS; ++i) { m.w_dw[i] = m.blob + o_dw[i]; m.w_pw[i] = m.blob + o_pw[i]; }
+  for (int i = 0; i <= m.n_blocks; ++i) { m.bn_scale[i] = m.blob + o_scale[i]; m.bn_shift[i] = m.blob + o_shift[i]; }
+  for (int i = 0; i < m.n_blocks; ++i) { m.w_dw[i] = m.blob + o_dw[i]; m.w_pw[i] = m.blob + o_pw[i]; }
+  m.tc_shift0 = m.blob + o_shift0_tc;
   m.w_d1 = m.blob + o_d1; m.b_d1 = m.blob + o_b1; m.w_d2 = m.blob + o_d2;
 
   // tensor-core operand images (fp16, pre-swizzled, BN scale folded in); the BN shift stays fp32
@@ -144,7 +164,7 @@ int model_build(kws_handle* h, int slot, int arch, const kws_tensor_h* t, int n)
 }
 
 // ---------------------------------------------------------------------------------------------
-// fp32 forward: conv1d_1 (implicit im2col GEMM) -> 11 x [depthwise prologue + pointwise GEMM +
+// fp32 forward: conv1d_1 (implicit im2col GEMM) -> 11 / 13 x [depthwise prologue + pointwise GEMM +
 // BN + ReLU6] -> head.  Activations are channels-last fp32 [rows, T, C], ping-ponged in the
 // handle's workspace; rows = clips_in_chunk * n_views, views of a clip adjacent.
 // ---------------------------------------------------------------------------------------------
@@ -177,7 +197,7 @@ int launch_forward_f32(kws_handle* h, Model& m, const float* wav, int B, const V
       KWS_LAUNCH_CHECK(h);
     }
     if (dbg_layer == 0) return launch_to_float(h, cur, false, dbg_out, static_cast<size_t>(rows) * m.t0 * m.c0, st);
-    for (int i = 0; i < NUM_BLOCKS; ++i) {
+    for (int i = 0; i < m.n_blocks; ++i) {
       const LayerDesc& d = m.layers[i];
       LoadDepthwise a{cur, m.w_dw[i], d.t_in, d.t_out, d.cin, d.stride, d.pad_left};
       EpiBnRelu6 e{nxt, m.bn_scale[i + 1], m.bn_shift[i + 1]};

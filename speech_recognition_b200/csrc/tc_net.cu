@@ -1611,8 +1611,8 @@ int launch_conv1_block1(kws_handle* h, Model& m, const float* wav, int nb, const
   p.w1_img = reinterpret_cast<const uint8_t*>(m.tc_conv1);
   p.w2_img = reinterpret_cast<const uint8_t*>(m.tc_pw[0]);
   p.dw_h = m.tc_dw[0];
-  p.shift1 = m.bn_shift[0]; p.shift2 = m.bn_shift[1];
-  p.c0 = m.c0; p.c1 = d.cout; p.t1 = m.t0; p.t2 = d.t_out;
+  p.shift1 = m.tc_shift0; p.shift2 = m.bn_shift[1];
+  p.c0 = m.c0_tc; p.c1 = d.cout; p.t1 = m.t0; p.t2 = d.t_out;
   p.blocks_per_view = (p.t2 + FUSE_ROWS - 1) / FUSE_ROWS;
   p.num_units = nb * vg.n_groups * p.blocks_per_view;
   const int rows = nb * V;
@@ -1647,8 +1647,8 @@ int launch_conv1_block1(kws_handle* h, Model& m, const float* wav, int nb, const
 bool fuse_conv1_block1(const Model& m) {
   static const bool off = [] { const char* e = getenv("KWS_NO_FUSE"); return e && e[0] == '1'; }();
   const LayerDesc& d = m.layers[0];
-  return !off && d.stride == 1 && d.cin == m.c0 && m.c0 % SLAB_K == 0 && m.c0 <= 128 && d.cout % 64 == 0 &&
-         2 * m.c0 + 2 * d.cout <= TMEM_COLS && d.t_out == m.t0 - 2;
+  return !off && d.stride == 1 && d.cin == m.c0 && m.c0_tc <= 128 && d.cout % 64 == 0 &&
+         2 * m.c0_tc + 2 * d.cout <= TMEM_COLS && d.t_out == m.t0 - 2;
 }
 
 }  // namespace
@@ -1656,32 +1656,45 @@ bool fuse_conv1_block1(const Model& m) {
 int model_build_tc(kws_handle* h, Model& m, const std::vector<std::vector<float>>& pw_host,
                    const std::vector<float>& conv1_host, const std::vector<std::vector<float>>& dw_host,
                    const std::vector<std::vector<float>>& scales) {
-  // conv1: fold the 3 overlapping patches into 80 taps: W80[u, co] = sum_f W[f, u - 20 f, co]
-  std::vector<float> w80(static_cast<size_t>(CONV1_K) * m.c0, 0.0f);
+  // conv1: fold the 3 overlapping patches into 80 taps: W80[u, co] = sum_f W[f, u - 20 f, co].  The tensor-core kernels
+  // work on 64-channel K slabs, so a conv1d_1 narrower than that (conv_1d_time_sliced: 32 filters) is padded to c0_tc
+  // with zero filters (zero BN shift: their activation is ReLU6(0) = 0) and block 1 gets zero taps / zero weight rows for them.
+  const int c0 = m.c0, c0p = m.c0_tc;
+  std::vector<float> w80(static_cast<size_t>(CONV1_K) * c0p, 0.0f), scale0(c0p, 1.0f);
+  std::copy(scales[0].begin(), scales[0].end(), scale0.begin());
   for (int f = 0; f < 3; ++f)
     for (int i = 0; i < 40; ++i)
-      for (int co = 0; co < m.c0; ++co)
-        w80[static_cast<size_t>(20 * f + i) * m.c0 + co] += conv1_host[static_cast<size_t>(f * 40 + i) * m.c0 + co];
+      for (int co = 0; co < c0; ++co)
+        w80[static_cast<size_t>(20 * f + i) * c0p + co] += conv1_host[static_cast<size_t>(f * 40 + i) * c0 + co];
   std::vector<__half> all, img;
   std::vector<size_t> offs, dw_offs;
   auto align_1k = [&]() { while (all.size() % 512) all.push_back(__float2half_rn(0.0f)); };   // 1024-byte aligned
-  build_weight_image(w80.data(), scales[0].data(), CONV1_K, m.c0, img);
+  build_weight_image(w80.data(), scale0.data(), CONV1_K, c0p, img);
   offs.push_back(all.size()); all.insert(all.end(), img.begin(), img.end());
-  for (int i = 0; i < NUM_BLOCKS; ++i) {
-    build_weight_image(pw_host[i].data(), scales[i + 1].data(), m.layers[i].cin, m.layers[i].cout, img);
+  for (int i = 0; i < m.n_blocks; ++i) {
+    const int cin = m.layers[i].cin, cinp = i == 0 ? c0p : cin, cout = m.layers[i].cout;
+    if (cinp == cin) {
+      build_weight_image(pw_host[i].data(), scales[i + 1].data(), cin, cout, img);
+    } else {
+      std::vector<float> padded(static_cast<size_t>(cinp) * cout, 0.0f);
+      std::copy(pw_host[i].begin(), pw_host[i].end(), padded.begin());      // rows cin .. cinp - 1 stay zero
+      build_weight_image(padded.data(), scales[i + 1].data(), cinp, cout, img);
+    }
     align_1k();
     offs.push_back(all.size()); all.insert(all.end(), img.begin(), img.end());
   }
-  for (int i = 0; i < NUM_BLOCKS; ++i) {                       // depthwise taps [3][cin] as fp16
+  for (int i = 0; i < m.n_blocks; ++i) {                       // depthwise taps [3][cin] as fp16
+    const int cin = m.layers[i].cin, cinp = i == 0 ? c0p : cin;
     align_1k();
     dw_offs.push_back(all.size());
-    for (float v : dw_host[i]) all.push_back(__float2half_rn(v));
+    for (int j = 0; j < 3; ++j)
+      for (int c = 0; c < cinp; ++c) all.push_back(__float2half_rn(c < cin ? dw_host[i][static_cast<size_t>(j) * cin + c] : 0.0f));
   }
   KWS_CUDA(h, cudaMalloc(&m.tc_blob, all.size() * sizeof(__half)));
   KWS_CUDA(h, cudaMemcpy(m.tc_blob, all.data(), all.size() * sizeof(__half), cudaMemcpyHostToDevice));
   __half* base = static_cast<__half*>(m.tc_blob);
   m.tc_conv1 = base + offs[0];
-  for (int i = 0; i < NUM_BLOCKS; ++i) { m.tc_pw[i] = base + offs[i + 1]; m.tc_dw[i] = base + dw_offs[i]; }
+  for (int i = 0; i < m.n_blocks; ++i) { m.tc_pw[i] = base + offs[i + 1]; m.tc_dw[i] = base + dw_offs[i]; }
   return KWS_OK;
 }
 
@@ -1731,19 +1744,20 @@ int launch_forward_tc(kws_handle* h, Model& m, const float* wav, int B, const Vi
       p.wav = wav + static_cast<size_t>(b0) * L; p.n_views = V;
       p.vg = vg;
       p.w_img = reinterpret_cast<const uint8_t*>(m.tc_conv1);
-      p.shift = m.bn_shift[0];
-      p.cin = CONV1_K; p.cout = m.c0; p.t_out = m.t0; p.rows_out = rows * m.t0;
+      p.shift = m.tc_shift0;
+      p.cin = CONV1_K; p.cout = m.c0_tc; p.t_out = m.t0; p.rows_out = rows * m.t0;
       p.tiles_per_group = (m.t0 + TILE_M - 1) / TILE_M;
       p.num_tiles = nb * vg.n_groups * p.tiles_per_group;
       p.num_kb = 2; p.last_ksteps = 1;
-      int rc = make_tensor_map(h, &p.tmap_out, cur, m.c0, m.t0, std::max(rows, 2), 32, true);   // 3-D: clip at t0
+      int rc = make_tensor_map(h, &p.tmap_out, cur, m.c0_tc, m.t0, std::max(rows, 2), 32, true);   // 3-D: clip at t0
       if (rc) return rc;
       rc = launch_tc_gemm<0>(h, p, st);
       if (rc) return rc;
     }
-    if (dbg_layer == 0) return launch_to_float(h, cur, true, dbg_out, static_cast<size_t>(rows) * m.t0 * m.c0, st);
-    for (int i = fused ? 1 : 0; i < NUM_BLOCKS; ++i) {
-      const LayerDesc& d = m.layers[i];
+    if (dbg_layer == 0) return launch_to_float(h, cur, true, dbg_out, static_cast<size_t>(rows) * m.t0 * m.c0_tc, st);   // c0_tc channels (zero padded)
+    for (int i = fused ? 1 : 0; i < m.n_blocks; ++i) {
+      LayerDesc d = m.layers[i];
+      if (i == 0) d.cin = m.c0_tc;                               // zero-padded conv1d_1 channels (zero taps, zero weight rows)
       if (d.cin % SLAB_K) return fail(h, KWS_EUNSUPPORTED, "channel count must be a multiple of 64");
       GemmParams p{};
       p.dw_h = m.tc_dw[i];

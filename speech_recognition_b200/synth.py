@@ -134,7 +134,7 @@ def raw_synthetic_weights(arch: int, seed: int | None = None, head_gain: float |
     """Seeded Glorot-uniform kernels with *uncalibrated* BatchNorm statistics."""
     rs = np.random.RandomState(arch if seed is None else seed)
     if head_gain is None:
-        head_gain = 32.0 if ARCHS[arch]["pool"] == "attn_mean" else 6.0
+        head_gain = {"attn_mean": 32.0, "gap_dense": 4.0}.get(ARCHS[arch]["pool"], 6.0)
     w = {}
     for name, shp in weight_shapes(arch).items():
         if name.endswith("/gamma"):

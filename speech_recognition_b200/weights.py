@@ -18,6 +18,8 @@ def infer_arch(weights: dict) -> int:
         return 195
     if c0 == 64 and classes == 32:
         return 106
+    if c0 == 32 and weights["dense_1/kernel"].shape[-1] == 256:
+        return 716                                   # conv_1d_time_sliced_model (model.py:716-772)
     raise ValueError(f"unrecognised network: conv1d_1 has {c0} filters, dense_2 has {classes} classes")
 
 

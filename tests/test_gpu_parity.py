@@ -482,3 +482,43 @@ def test_config4_and_config5_pipelines(engine):
     # fallback rule: where all three disagree the first model's label is kept
     alldiff = (labels[0] != labels[1]) & (labels[0] != labels[2]) & (labels[1] != labels[2])
     assert np.array_equal(voted.cpu().numpy()[alldiff], labels[0][alldiff])
+
+
+# --------------------------------------------------------------------------- conv_1d_time_sliced_model
+def test_time_sliced_family(engine):
+    """conv_1d_time_sliced_model(filter_mult=1) (model.py:716-772): conv1d_1 with 32 filters, 13 depthwise-separable
+    blocks, GlobalAveragePooling1D -> Dense(256) -> ReLU6 -> Dense(12) head, through the same kernels: fp32 tier to 1e-4
+    with exact labels, tensor-core tier (conv1d_1 zero-padded to one 64-channel K slab) layer by layer and end to end."""
+    from speech_recognition_b200 import arch as A
+    w = synth.synthetic_weights(716)
+    assert engine.load_model(2, 716, w) == 12
+    x = synth.make_clips(24, seed=716)
+    xt = dev(x)
+    r_probs, r_pred = driver.tta_predict(lambda v: network.forward(v, w, 716, dtype=torch.float64), x, TTA_8)
+    engine.set_precision("fp32")
+    probs, amax = engine.forward(xt, views=TTA_8, slot=2)
+    np.testing.assert_allclose(probs.cpu().numpy(), r_probs, rtol=1e-4, atol=1e-5)
+    assert np.array_equal(amax.cpu().numpy(), r_pred)
+    _, _, acts = network.forward(x[:4], w, 716, dtype=torch.float64, return_activations=True)
+    Ts = A.layer_lengths(716)[1:]
+    got = engine.debug_activation(xt[:4], 13, (Ts[13], 512), slot=2).cpu().numpy()
+    assert got.shape == acts[13].shape == (4, 3, 512) and np.abs(got - acts[13]).max() < 1e-4
+    engine.set_precision("tc")
+    try:
+        for layer in (1, 2, 7, 13):                                  # layer 0 has 64 (zero-padded) channels in this tier
+            got = engine.debug_activation(xt[:4], layer, (Ts[layer], acts[layer].shape[2]), slot=2).cpu().numpy()
+            err = np.abs(got - acts[layer])
+            assert got.shape == acts[layer].shape and err.max() < 6 * 1.5e-2 and err.mean() < 4e-3, (layer, err.max(), err.mean())
+        pad = engine.debug_activation(xt[:4], 0, (Ts[0], 64), slot=2).cpu().numpy()
+        assert np.abs(pad[:, :, :32] - acts[0]).max() < 2e-2 and not pad[:, :, 32:].any()
+        for fuse in (True, False):
+            engine.set_fusion(fuse)
+            probs, amax = engine.forward(xt, views=TTA_8, slot=2)
+            err = np.abs(probs.cpu().numpy() - r_probs)
+            assert np.quantile(err, 0.99) < 1e-2 and err.max() < 0.1, (fuse, np.quantile(err, 0.99), err.max())
+            srt = np.sort(r_probs, axis=1)
+            confident = (srt[:, -1] - srt[:, -2]) > 0.1
+            assert (amax.cpu().numpy()[confident] == r_pred[confident]).all()
+    finally:
+        engine.set_fusion(True)
+        engine.set_precision("fp32")

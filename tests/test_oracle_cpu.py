@@ -213,3 +213,38 @@ def test_contrib_audio_restatement_properties():
         if band[i] + 1 < 40:
             dense[i, band[i] + 1] += 1 - w[i]
     assert np.allclose(e, dense.sum(0), rtol=1e-6)
+
+
+def test_time_sliced_oracle_against_independent_torch_module():
+    """conv_1d_time_sliced_model (model.py:716-772) restated twice: oracle.network.forward(arch=716) vs a plain
+    torch.nn stack built here from the reference's builder, on the same Keras-named weights."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import network
+    from speech_recognition_b200 import synth
+    w = synth.synthetic_weights(716)
+    x = torch.from_numpy(synth.make_clips(3, seed=4)).double()
+    # overlapping_time_slice_stack(x, 40, 20): SAME patches, then Conv1D(32, 3, strides=2) over the patch axis
+    p = F.pad(x, (10, 10)).unfold(1, 40, 20)                                   # [B,800,40]
+    k = torch.as_tensor(w["conv1d_1/kernel"]).double()                          # [3,40,32]
+    y = torch.stack([sum(p[:, 2 * j + f] @ k[f] for f in range(3)) for j in range(399)], 1)   # [B,399,32]
+
+    def bn_relu6(y, i):
+        g, b, m, v = (torch.as_tensor(w[f"batch_normalization_{i}/{n}"]).double() for n in ("gamma", "beta", "moving_mean", "moving_variance"))
+        return torch.clamp((y - m) / torch.sqrt(v + 1e-3) * g + b, 0, 6)
+    y = bn_relu6(y, 1)
+    for i, (co, s) in enumerate(network.ARCHS[716]["blocks"], start=1):
+        d = torch.as_tensor(w[f"depthwise_conv2d_{i}/depthwise_kernel"]).double()[0, :, :, 0]   # [3,C]
+        T = y.shape[1]
+        if s == 2:
+            out = -(-T // 2); total = max((out - 1) * 2 + 3 - T, 0)
+            y = F.pad(y, (0, 0, total // 2, total - total // 2))
+        else:
+            out = T - 2
+        y = sum(y[:, j:j + s * (out - 1) + 1:s] * d[j] for j in range(3))
+        y = bn_relu6(y @ torch.as_tensor(w[f"conv1d_{i + 1}/kernel"]).double()[0], i + 1)
+    assert y.shape == (3, 3, 512)
+    z = torch.clamp(y.mean(1) @ torch.as_tensor(w["dense_1/kernel"]).double(), 0, 6)
+    ref = torch.softmax(z @ torch.as_tensor(w["dense_2/kernel"]).double(), -1).numpy()
+    got = network.forward(x.numpy(), w, 716, dtype=torch.float64)
+    np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-12)

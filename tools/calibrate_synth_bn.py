@@ -61,7 +61,7 @@ def calibrate(arch, clips):
 def main():
     clips = synth.make_clips(96, seed=synth.SEED + 1000)
     clips = np.concatenate([clips, 1.2 * clips[:16], 0.9 * clips[16:32]]).astype(np.float32)
-    for key, seeds in ((195, (195, 206)), (106, (106,))):
+    for key, seeds in ((195, (195, 206)), (106, (106,)), (716, (716,))):
         out = {}
         for s in seeds:
             stats, w = calibrate(s, clips)
