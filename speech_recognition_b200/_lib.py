@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libkws.so")
+LIB_PATH = os.environ.get("KWS_LIBKWS") or os.path.join(HERE, "libkws.so")   # KWS_LIBKWS: e.g. the profiling build libkws_prof.so
 
 FEAT_RAW, FEAT_SPEC, FEAT_LOGMEL, FEAT_MFCC = -1, 0, 1, 2
 PREC_FP32, PREC_TC = 0, 1

@@ -10,11 +10,14 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "csrc", "_obj")
-LIB = os.path.join(HERE, "libkws.so")
+PROFILE = os.environ.get("KWS_PROFILE_BUILD", "0") not in ("", "0")
+# the profiling build (knockout switches + event traces compiled in) is a SECOND library, libkws_prof.so, selected at
+# run time with KWS_LIBKWS=<path>: both travel to the GPU box, so an A/B visit does not spend GPU minutes compiling
+OBJ = os.path.join(HERE, "csrc", "_obj_prof" if PROFILE else "_obj")
+LIB = os.path.join(HERE, "libkws_prof.so" if PROFILE else "libkws.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
-if os.environ.get("KWS_PROFILE_BUILD", "0") not in ("", "0"):       # knockout switches + event trace in the block kernel
+if PROFILE:                                                          # knockout switches + event trace in the kernels
     NVCC_FLAGS.append("-DKWS_PROFILE_BUILD=1")
 if os.environ.get("KWS_FIR_FP16", "0") not in ("", "0"):            # A/B aid: the r01 packed-half depthwise FIR
     NVCC_FLAGS.append("-DKWS_FIR_FP16=1")

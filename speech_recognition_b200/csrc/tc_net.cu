@@ -931,6 +931,8 @@ struct alignas(64) FusedParams {
   int c0, c1, t1, t2;        // channels; rows per clip-view after conv1d_1 (399) / after block 1 (397)
   int blocks_per_view;       // ceil(t2 / 126)
   int num_units;             // clips * view groups * blocks_per_view
+  int knockout;              // KWS_FKNOCK (profiling build only, results become wrong): 1 output warps skip conversion + store,
+                             // 2 middle warps skip the FIR, 4 no TMA stores, 8 no pointwise MMAs
 };
 
 struct FusedSmem { uint32_t a1, w1, w2, a2, raw, out, win, sh1, sh2, taps, bars, total; };
@@ -1111,7 +1113,7 @@ __global__ void __launch_bounds__(FuseRoles<kT>::THREADS, 1) conv1_block1_kernel
         const float gain = p.vg.gain[mem];
         const int bsel = n2 & 1;
         mbar_wait(&a2_empty[bsel], (static_cast<uint32_t>(n2 >> 1) & 1u) ^ 1u);   // the MMA of view n2 - 2 has read this buffer
-        if (on) {
+        if (on && !(kProfile && (p.knockout & 2))) {
           const uint32_t bo = static_cast<uint32_t>(bsel) * buf_bytes;
           // y[t] = fp16(relu6(gain * acc + shift)) -- the rounding the unfused path stores -- as packed pairs (y[2i], y[2i+1])
           auto ypair = [&](int ip) -> uint32_t {
@@ -1253,13 +1255,13 @@ __global__ void __launch_bounds__(FuseRoles<kT>::THREADS, 1) conv1_block1_kernel
             tmem_ld_wait();
             const bool more = c0 + c_step < p.c1;
             if (!more) { tc_fence_before(); mbar_arrive(&acc2_empty[s2]); }   // every column of this view is in registers
-            epilogue_chunk<false>(va, s_sh2 + c0, row_base, 0, lane & 7, 1.0f);
+            if (!(kProfile && (p.knockout & 1))) epilogue_chunk<false>(va, s_sh2 + c0, row_base, 0, lane & 7, 1.0f);
             if (more) tmem_ld32(taddr + c0 + c_step, va);
-            epilogue_chunk<false>(vb, s_sh2 + c0 + 32, row_base, 4, lane & 7, 1.0f);
+            if (!(kProfile && (p.knockout & 1))) epilogue_chunk<false>(vb, s_sh2 + c0 + 32, row_base, 4, lane & 7, 1.0f);
             if (more) tmem_ld32(taddr + c0 + c_step + 32, vb);
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && !(kProfile && (p.knockout & 5))) {
               tma_store_3d(q == 3 ? &p.tmap_out30 : &p.tmap_out, c0, row0, rv, box);
               bulk_commit_group();
             }
@@ -1326,7 +1328,9 @@ __global__ void __launch_bounds__(FuseRoles<kT>::THREADS, 1) conv1_block1_kernel
           tc_fence_after();
           const uint32_t d = tmem_base + acc2_col0 + static_cast<uint32_t>(s2 * p.c1);
           uint32_t a = a2 + static_cast<uint32_t>(s2) * a2_buf_lo, w = w2;
-          if constexpr (kT) {
+          if (kProfile && (p.knockout & 8)) {
+            umma_commit_elect(a2_empty0 + 8u * s2); umma_commit_elect(acc2_full0 + 8u * s2);
+          } else if constexpr (kT) {
             // A2 is MN-major (see the middle warps): a K = 16 step spans two 8-channel groups = 2 SBO, a 64-channel slab 8 SBO
             a = umma_desc_lo_mn(smem_u32(a2_base), FUSE_A2_LBO) + static_cast<uint32_t>(s2) * a2_buf_lo;
             for (int kb = 0; kb < nkb2; ++kb, a += (8 * FUSE_A2_SBO) >> 4, w += w2_slab)
@@ -1632,6 +1636,8 @@ int launch_conv1_block1(kws_handle* h, Model& m, const float* wav, int nb, const
   // c0 == 128: the transposed form (see the kernel); KWS_FUSE_V1=1 keeps the r01 row-major form for A/B runs
   static const bool v1 = [] { const char* e = getenv("KWS_FUSE_V1"); return e && e[0] == '1'; }();
   const bool transposed = !v1 && p.c0 == TILE_M;
+  static const int fknock = [] { const char* e = getenv("KWS_FKNOCK"); return e && kProfile ? atoi(e) : 0; }();
+  p.knockout = fknock;
   KWS_T0(h, KC_CONV1, st);
   if (transposed) conv1_block1_kernel<true><<<grid, FuseRoles<true>::THREADS, lay.total, st>>>(p);
   else conv1_block1_kernel<false><<<grid, FuseRoles<false>::THREADS, lay.total, st>>>(p);

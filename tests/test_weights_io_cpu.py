@@ -60,6 +60,23 @@ def test_hdf5_rejects_other_files(tmp_path):
         hdf5_reader.File(str(p))
 
 
+def test_hdf5_reader_on_a_file_written_by_libhdf5():
+    """The one file in this image that a REAL libhdf5 wrote: scipy ships MATLAB's v7.3 test file, which is an HDF5 file
+    behind a 512-byte user block (superblock search, symbol-table group, v1 object header with attribute, contiguous
+    float64 dataset -- the same structures h5py 2.x / libhdf5 1.8 emit for a Keras checkpoint).  scipy's own test suite
+    documents its content: testdouble = 0 : pi/4 : 2*pi.  (h5py is not installed and the reference's checkpoints are
+    not in the mount, so this is the independent pin there is; tests/h5_writer.py covers the Keras layout itself.)"""
+    import scipy.io
+    path = os.path.join(os.path.dirname(scipy.io.__file__), "matlab", "tests", "data", "testhdf5_7.4_GLNX86.mat")
+    if not os.path.exists(path):
+        pytest.skip("scipy's MATLAB v7.3 test file is not installed")
+    with hdf5_reader.File(path) as f:
+        assert list(f.keys()) == ["testdouble"]
+        d = f["testdouble"]
+        assert d.shape == (9, 1) and d.dtype == np.float64 and d.attrs["MATLAB_class"] == b"double"
+        np.testing.assert_allclose(d.read()[:, 0], np.arange(9) * np.pi / 4, rtol=0, atol=1e-15)
+
+
 @pytest.mark.parametrize("arch", [195, 106])
 def test_keras_checkpoint_to_weights(tmp_path, arch):
     w = synth.synthetic_weights(arch)
