@@ -10,7 +10,7 @@ the north-star stages in front of it -- one "step" is one pass over a batch of B
 clips: augment (time-shift + noise mix + volumes) -> log-mel (40 mel, 30 ms / 10 ms) -> 8-view forward
 -> TTA mean -> argmax.  B clips x 64 KB = 1.05 GB at the default B=16384 (about the per-GPU share of
 the 158,538-clip job on 8 GPUs), far larger than the 126 MB L2; the forward runs in chunks of
---max-rows clip-views (32768 = 4096 clips).
+--max-rows clip-views (65536 = 8192 clips: two chunks per step; r01 used 32768).
 Per-GPU work is fixed as N grows (weak scaling); the only collective is one all-gather of the
 [B,12] probabilities per step.  `value` times the device-resident path with CUDA events on the
 launching stream (max over ranks); `e2e` times the host-buffer C-ABI call with the same work: clips in the
@@ -701,7 +701,7 @@ def main():
     ap.add_argument("--config", type=int, default=3, choices=[2, 3, 4, 5], help="BASELINE.json config (1-based); default 3 = the headline")
     ap.add_argument("--job", action="store_true", help="config 3: the fixed 158,538-clip job as one step (strong scaling)")
     ap.add_argument("--batch", type=int, default=None, help="clips per GPU per step (default 16384; config 2: 4096)")
-    ap.add_argument("--max-rows", type=int, default=32768, help="clip-views per internal chunk")
+    ap.add_argument("--max-rows", type=int, default=65536, help="clip-views per internal chunk (r01: 32768)")
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")

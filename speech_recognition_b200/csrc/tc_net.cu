@@ -108,7 +108,7 @@ struct alignas(64) GemmParams {
   int prefetch_tiles;       // how many of this CTA's tiles ahead the raw loader prefetches into L2 (0 = off)
   unsigned long long* trace;   // KWS_TRACE=<block index> (profiling only): per-role event log of CTA 0, see trace_ev
   int knockout;             // KWS_KNOCKOUT (profiling only, results become wrong): 1 no TMA stores, 2 no FIR,
-                            // 4 no MMAs, 8 no epilogue math, 16 no raw loads
+                            // 4 no MMAs, 8 no epilogue math, 16 no raw loads, 32 no weight loads
   // B side: pre-swizzled fp16 blocks of n_inst rows x 128 B, block j = (kb, nh) = (j / n_halves, j % n_halves)
   const uint8_t* w_img;
   // epilogue
@@ -727,6 +727,7 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
     // =========================== weight loader ===========================
     if (lane == 0) {
       auto load_block = [&](int j, int slot, uint64_t* bar) {
+        if (kProfile && (p.knockout & 32)) { mbar_arrive(bar); return; }   // no weight traffic (stale smem as weights)
         mbar_arrive_expect_tx(bar, b_block_bytes);
         // image = [K slab][cout rows x 128 B]; block j = (K slab j / n_halves, rows col0 + (j % n_halves) * n_inst ...)
         const uint8_t* src = p.w_img + (static_cast<size_t>(j / p.n_halves) * p.cout + col0 + (j % p.n_halves) * p.n_inst) * ROW_BYTES;
@@ -1244,21 +1245,28 @@ __global__ void __launch_bounds__(FuseRoles<kT>::THREADS, 1) conv1_block1_kernel
         if (row0 < p.t2 && c_first < p.c1) {
           const int rv = b * p.n_views + p.vg.view[mem];
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc2_col0 + static_cast<uint32_t>(s2 * p.c1);
+          // 32 columns per step, two register buffers: the load of step s + 1 is issued right after the wait of step s
+          // and flies under the conversion of step s (tcgen05.wait::ld waits for ALL loads of the thread, so a load can
+          // only overlap math that does not need it).  The four output warps run in lock step: without this the TMEM read
+          // port (64 B / cycle / SM) idles while they convert and they idle while it reads (r02 knockouts: the two add up).
           uint32_t va[32], vb[32];
-          tmem_ld32(taddr + c_first, va);
-          tmem_ld32(taddr + c_first + 32, vb);
-          for (int c0 = c_first; c0 < p.c1; c0 += c_step) {
+          const int n_steps = (p.c1 - c_first + c_step - 1) / c_step * 2;       // 32-column steps of this warp
+          auto col_of = [&](int st) { return c_first + (st >> 1) * c_step + (st & 1) * 32; };
+          tmem_ld32(taddr + col_of(0), va);
+          for (int st = 0; st < n_steps; st += 2) {
             uint8_t* box = box0 + ob * OUT_STAGE_BYTES;
             uint8_t* row_base = box + lane * ROW_BYTES;
+            const int c0 = col_of(st);
             if (lane == 0) bulk_wait_group_read<kBoxes - 1>();   // the store that last used this box has read it
             __syncwarp();
             tmem_ld_wait();
-            const bool more = c0 + c_step < p.c1;
-            if (!more) { tc_fence_before(); mbar_arrive(&acc2_empty[s2]); }   // every column of this view is in registers
+            tmem_ld32(taddr + col_of(st + 1), vb);
             if (!(kProfile && (p.knockout & 1))) epilogue_chunk<false>(va, s_sh2 + c0, row_base, 0, lane & 7, 1.0f);
-            if (more) tmem_ld32(taddr + c0 + c_step, va);
+            tmem_ld_wait();
+            const bool more = st + 2 < n_steps;
+            if (more) tmem_ld32(taddr + col_of(st + 2), va);
+            else { tc_fence_before(); mbar_arrive(&acc2_empty[s2]); }   // every column of this view is in registers
             if (!(kProfile && (p.knockout & 1))) epilogue_chunk<false>(vb, s_sh2 + c0 + 32, row_base, 4, lane & 7, 1.0f);
-            if (more) tmem_ld32(taddr + c0 + c_step + 32, vb);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0 && !(kProfile && (p.knockout & 5))) {
