@@ -58,6 +58,10 @@ extern "C" {
                                       filters, 13 depthwise-separable blocks, GlobalAveragePooling1D -> Dense(256)
                                       -> ReLU6 -> Dense(num_classes) head; num_classes = dense_2/kernel.shape[1] */
 
+#define KWS_ARCH_STEFFENET 1663    /* steffeNet, model.py:1663-1726 (Conv1D k75 s50 stem, residual depthwise-separable blocks
+                                      up to 1536 channels, max || average pooling head).  Runs on the fp32 CUDA-core kernels in
+                                      both precision tiers (channel counts beyond the tensor-core kernels' tiling). */
+
 typedef struct kws_handle kws_t;
 
 /* A host fp32 tensor addressed by its Keras variable name, e.g.

@@ -160,3 +160,88 @@ def forward(x, w, arch: int = 195, dtype=torch.float32, return_activations: bool
     if return_activations:
         return probs.numpy(), logits.numpy(), [t.transpose(1, 2).contiguous().numpy() for t in acts]
     return probs.numpy()
+
+
+# ---------------------------------------------------------------------------------------------
+# steffeNet (model.py:1663-1726): Conv1D(256, 75, strides=50, SAME) on the raw waveform -> BN -> ReLU6 -> one SAME
+# depthwise-separable block -> 6 x [residual block (stride 2, 1x1 strided shortcut + BN), residual block (identity
+# shortcut)], each residual block = two SAME depthwise-separable blocks + Add -> GlobalMaxPooling || GlobalAveragePooling
+# -> Dense(num_classes, softmax, no bias).  Keras numbers the layers in creation order: the shortcut Conv1D / BN of a
+# stride-2 residual block are created BEFORE the block's depthwise / pointwise layers.
+# ---------------------------------------------------------------------------------------------
+STEFFE_WIDTHS = (320, 384, 512, 768, 1024, 1536)
+
+
+def steffenet_plan():
+    """[(kind, ...)] in layer-creation order with the Keras layer numbers each step consumes."""
+    plan, conv, bn, dw = [], 1, 1, 0
+    plan.append(("conv75", conv, bn)); conv += 1; bn += 1
+    dw += 1; plan.append(("dwpw", dw, conv, bn, 1)); conv += 1; bn += 1
+    for nh in STEFFE_WIDTHS:
+        for stride in (2, 1):
+            if stride == 2:
+                plan.append(("shortcut", conv, bn)); conv += 1; bn += 1
+            else:
+                plan.append(("identity",))
+            dw += 1; plan.append(("dwpw", dw, conv, bn, stride)); conv += 1; bn += 1
+            dw += 1; plan.append(("dwpw", dw, conv, bn, 1)); conv += 1; bn += 1
+            plan.append(("add",))
+    return plan
+
+
+def steffenet_weight_shapes(classes: int = 12):
+    shapes, c = {}, 256
+
+    def bn(i, ch):
+        for nm in ("gamma", "beta", "moving_mean", "moving_variance"):
+            shapes[f"batch_normalization_{i}/{nm}"] = (ch,)
+    widths = iter(w for w in STEFFE_WIDTHS for _ in range(2))
+    nh = c
+    for step in steffenet_plan():
+        if step[0] == "conv75":
+            shapes[f"conv1d_{step[1]}/kernel"] = (75, 1, 256); bn(step[2], 256)
+        elif step[0] in ("shortcut", "identity"):
+            nh = next(widths)
+            if step[0] == "shortcut":
+                shapes[f"conv1d_{step[1]}/kernel"] = (1, c, nh); bn(step[2], nh)
+        elif step[0] == "dwpw":
+            shapes[f"depthwise_conv2d_{step[1]}/depthwise_kernel"] = (1, 3, c, 1)
+            shapes[f"conv1d_{step[2]}/kernel"] = (1, c, nh); bn(step[3], nh)
+            c = nh
+    shapes["dense_1/kernel"] = (2 * c, classes)
+    return shapes
+
+
+def forward_steffenet(x, w, dtype=torch.float64):
+    """x [B,16000] -> softmax probabilities [B,classes] (channels-first internally)."""
+    x = torch.as_tensor(np.asarray(x), dtype=dtype)
+
+    def bnorm(y, i, relu6=True):
+        g, b, m, v = (torch.as_tensor(w[f"batch_normalization_{i}/{n}"], dtype=dtype) for n in ("gamma", "beta", "moving_mean", "moving_variance"))
+        sc = torch.rsqrt(v + BN_EPS) * g
+        y = y * sc[None, :, None] + (b - m * sc)[None, :, None]
+        return torch.clamp(y, 0.0, 6.0) if relu6 else y
+    y, res = None, None
+    for step in steffenet_plan():
+        if step[0] == "conv75":
+            k = torch.as_tensor(w[f"conv1d_{step[1]}/kernel"], dtype=dtype)            # [75,1,256]
+            out, pl, pr = same_pad(x.shape[1], 75, 50)
+            y = F.conv1d(F.pad(x, (pl, pr))[:, None, :], k.permute(2, 1, 0).contiguous(), stride=50)
+            y = bnorm(y, step[2])
+        elif step[0] == "shortcut":
+            k = torch.as_tensor(w[f"conv1d_{step[1]}/kernel"], dtype=dtype)[0]         # [C,nh]
+            res = bnorm(F.conv1d(y, k.t()[:, :, None].contiguous(), stride=2), step[2], relu6=False)
+        elif step[0] == "identity":
+            res = y
+        elif step[0] == "dwpw":
+            _, dwi, ci, bi, stride = step
+            dk = torch.as_tensor(w[f"depthwise_conv2d_{dwi}/depthwise_kernel"], dtype=dtype)
+            C = dk.shape[2]
+            _, pl, pr = same_pad(y.shape[-1], 3, stride)
+            y = F.conv1d(F.pad(y, (pl, pr)), dk[0, :, :, 0].t().reshape(C, 1, 3).contiguous(), stride=stride, groups=C)
+            pk = torch.as_tensor(w[f"conv1d_{ci}/kernel"], dtype=dtype)[0]
+            y = bnorm(F.conv1d(y, pk.t()[:, :, None].contiguous()), bi)
+        else:
+            y = y + res
+    z = torch.cat([y.max(dim=2).values, y.mean(dim=2)], dim=1)
+    return torch.softmax(z @ torch.as_tensor(w["dense_1/kernel"], dtype=dtype), dim=-1).numpy()

@@ -30,6 +30,46 @@ ARCHS[TIME_SLICED] = dict(conv1=32, blocks=[(64, 1), (128, 2), (128, 1), (192, 2
                           dense1_bias=False, pool="gap_dense", hidden=256, classes=12)
 
 
+# steffeNet (reference model.py:1663-1726): Conv1D(256, 75, strides=50) stem, one SAME depthwise-separable block, then per
+# width two residual blocks (the first with stride 2 and a strided 1x1 shortcut + BN), max || average pooling, Dense.
+STEFFENET = 1663
+STEFFE_WIDTHS = (320, 384, 512, 768, 1024, 1536)
+ARCHS[STEFFENET] = dict(conv1=256, blocks=[], dense1_bias=False, pool="max_avg_dense", classes=12)
+
+
+def steffenet_weight_shapes(classes: int = 12):
+    """Keras variable names / shapes in layer-creation order: the shortcut Conv1D / BN of a stride-2 residual block are
+    created before the block's depthwise / pointwise layers."""
+    shapes, c = {}, 256
+    conv, bn, dw = 1, 1, 0
+
+    def add_bn(ch):
+        nonlocal bn
+        for nm in ("gamma", "beta", "moving_mean", "moving_variance"):
+            shapes[f"batch_normalization_{bn}/{nm}"] = (ch,)
+        bn += 1
+
+    def add_dwpw(cout):
+        nonlocal conv, dw, c
+        dw += 1
+        shapes[f"depthwise_conv2d_{dw}/depthwise_kernel"] = (1, 3, c, 1)
+        shapes[f"conv1d_{conv}/kernel"] = (1, c, cout); conv += 1
+        add_bn(cout)
+        c = cout
+    shapes["conv1d_1/kernel"] = (75, 1, 256); conv += 1
+    add_bn(256)
+    add_dwpw(256)
+    for nh in STEFFE_WIDTHS:
+        for stride in (2, 1):
+            if stride == 2:
+                shapes[f"conv1d_{conv}/kernel"] = (1, c, nh); conv += 1
+                add_bn(nh)
+            add_dwpw(nh)
+            add_dwpw(nh)
+    shapes["dense_1/kernel"] = (2 * c, classes)
+    return shapes
+
+
 def same_pad(T: int, k: int, s: int):
     """TF 'SAME': out = ceil(T/s), pad_left = pad_total // 2."""
     out = -(-T // s)
@@ -49,6 +89,8 @@ def layer_lengths(arch: int, input_size: int = INPUT_SAMPLES):
 
 
 def weight_shapes(arch: int):
+    if arch == STEFFENET:
+        return steffenet_weight_shapes(ARCHS[arch]["classes"])
     a = ARCHS[arch]
     shapes = {}
     c = a["conv1"]

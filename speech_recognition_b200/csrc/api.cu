@@ -65,6 +65,7 @@ int forward_dispatch(kws_handle* h, int slot, const float* wav, int B, const Vie
   if (B < 0) return fail(h, KWS_EINVAL, "negative batch");
   if (B == 0) return KWS_OK;
   if (!wav) return fail(h, KWS_EINVAL, "null waveform pointer");
+  if (h->models[slot].arch == KWS_ARCH_STEFFENET) return launch_forward_steffe(h, h->models[slot], wav, B, vt, probs, argmax, st);
   return h->precision == KWS_PREC_FP32 ? launch_forward_f32(h, h->models[slot], wav, B, vt, probs, argmax, st)
                                        : launch_forward_tc(h, h->models[slot], wav, B, vt, probs, argmax, st);
 }
@@ -136,6 +137,7 @@ void kws_destroy(kws_t* h) {
     if (h->models[i].blob) cudaFree(h->models[i].blob);
     if (h->models[i].tc_blob) cudaFree(h->models[i].tc_blob);
     if (h->models[i].hidden_ws) cudaFree(h->models[i].hidden_ws);
+    if (h->models[i].steffe) steffe_free(h->models[i].steffe);
   }
   if (h->fe.blob) cudaFree(h->fe.blob);
   if (h->fe.tc_blob) cudaFree(h->fe.tc_blob);
@@ -332,6 +334,7 @@ int kws_debug_activation(kws_t* h, int slot, const float* wav, int B, const int3
   int rc = make_views(h, view_shift_h, view_gain_h, n_views, &vt);
   if (rc) return rc;
   if (slot < 0 || slot >= KWS_MAX_MODELS || !h->models[slot].loaded) return fail(h, KWS_ESTATE, "model not loaded");
+  if (h->models[slot].arch == KWS_ARCH_STEFFENET) return fail(h, KWS_EUNSUPPORTED, "kws_debug_activation is not available for steffeNet");
   if (layer < 0 || layer > h->models[slot].n_blocks || !out || !wav || B <= 0) return fail(h, KWS_EINVAL, "bad arguments");
   if (B * n_views > h->max_rows) return fail(h, KWS_EINVAL, "debug activation needs B*n_views <= max_rows");
   cudaStream_t st = static_cast<cudaStream_t>(stream);

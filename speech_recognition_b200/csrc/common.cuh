@@ -11,6 +11,7 @@
 
 namespace kws {
 
+struct SteffeNet;
 constexpr int L = KWS_SAMPLES;           // samples per clip
 constexpr int MAX_BLOCKS = 13;           // depthwise-separable blocks after conv1d_1: 11 (exp 195 / 206 / 106) or 13 (conv_1d_time_sliced)
 constexpr int TIMED_BLOCKS = 11;         // blocks with their own kws_timing_read slot
@@ -44,6 +45,7 @@ struct Model {
   float* w_dw[MAX_BLOCKS];                // [3, cin]
   float* w_pw[MAX_BLOCKS];                // [cin, cout]
   float* tc_shift0 = nullptr;             // conv1d_1 BN shift padded to c0_tc (== bn_shift[0] when c0 is a multiple of 64)
+  struct SteffeNet* steffe = nullptr;     // arch KWS_ARCH_STEFFENET: its own layer program (steffenet.cu)
   float* hidden_ws = nullptr;             // head_kind 1: [max rows][hidden] activations of the hidden Dense layer
   size_t hidden_ws_rows = 0;
   float* w_d1 = nullptr;                  // [t_last*c_last, t_last]  (head_kind 1: [c_last, hidden])
@@ -178,6 +180,14 @@ int launch_augment(kws_handle* h, const float* wav, const int16_t* pcm, float pc
                    const int32_t* shift, const int32_t* bg_file, const int32_t* bg_off,
                    const float* bg_vol, const float* fg_vol, float* out, int B, int clamp,
                    cudaStream_t st);
+int launch_dense_softmax_tta(kws_handle* h, const float* hid, int hidden, int n_views, int n_clips, const float* w2, int classes,
+                             float* probs_mean, int32_t* argmax, cudaStream_t st);   // Dense(classes, softmax) per view + TTA mean + argmax
+// steffeNet (model.py:1663-1726), fp32 CUDA-core kernels (steffenet.cu)
+struct SteffeNet;
+int steffe_build(kws_handle* h, Model& m, const kws_tensor_h* t, int n);
+void steffe_free(SteffeNet* s);
+int launch_forward_steffe(kws_handle* h, Model& m, const float* wav, int B, const ViewTable& vt, float* probs_mean, int32_t* argmax,
+                          cudaStream_t st);
 int launch_time_stretch(kws_handle* h, const int16_t* pcm, int B, double rate, float divisor, int16_t* out, cudaStream_t st);
 int frontend_build(kws_handle* h, int win, int hop, int n_mel, int n_keep, float f_lo, float f_hi,
                    int sample_rate, int flavour = 0);

@@ -281,11 +281,15 @@ struct EpiRelu6 {            // Dense(256, use_bias=False) -> Activation(relu6)
 namespace {
 // Dense(classes, softmax, no bias) per view, TTA mean in view order, first-index argmax: one warp per clip
 __global__ void __launch_bounds__(256) dense_softmax_tta_kernel(const float* __restrict__ hid, int hidden, int n_views, int n_clips,
-                                                                const float* __restrict__ w2, int classes,
+                                                                const float* __restrict__ w2, int classes, int w_in_smem,
                                                                 float* __restrict__ probs_mean, int32_t* __restrict__ argmax) {
-  extern __shared__ float s_w2[];                         // [hidden][classes]
-  for (int i = threadIdx.x; i < hidden * classes; i += blockDim.x) s_w2[i] = __ldg(&w2[i]);
-  __syncthreads();
+  extern __shared__ float s_w2_buf[];                     // [hidden][classes] when it fits (w_in_smem), else read through L1 / L2
+  const float* s_w2 = w2;
+  if (w_in_smem) {
+    for (int i = threadIdx.x; i < hidden * classes; i += blockDim.x) s_w2_buf[i] = __ldg(&w2[i]);
+    __syncthreads();
+    s_w2 = s_w2_buf;
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   for (int b = blockIdx.x * wpb + warp; b < n_clips; b += gridDim.x * wpb) {
     float acc_p = 0.0f;
@@ -317,6 +321,19 @@ __global__ void __launch_bounds__(256) dense_softmax_tta_kernel(const float* __r
 }
 }  // namespace
 
+int launch_dense_softmax_tta(kws_handle* h, const float* hid, int hidden, int n_views, int n_clips, const float* w2, int classes,
+                             float* probs_mean, int32_t* argmax, cudaStream_t st) {
+  if (classes > HEAD_MAX_CLASSES) return fail(h, KWS_EUNSUPPORTED, "too many classes");
+  const size_t w_bytes = static_cast<size_t>(hidden) * classes * sizeof(float);
+  const int in_smem = w_bytes <= 48 * 1024 ? 1 : 0;
+  const int grid = std::max(1, std::min(4 * h->num_sms, (n_clips + 7) / 8));
+  KWS_T0(h, KC_HEAD, st);
+  dense_softmax_tta_kernel<<<grid, 256, in_smem ? w_bytes : 0, st>>>(hid, hidden, n_views, n_clips, w2, classes, in_smem, probs_mean, argmax);
+  KWS_T1(h, st);
+  KWS_LAUNCH_CHECK(h);
+  return KWS_OK;
+}
+
 static int launch_head_gap_dense(kws_handle* h, Model& m, const void* act, bool act_half, int n_clips, int n_views,
                                  float* probs_mean, int32_t* argmax, cudaStream_t st) {
   const int rows = n_clips * n_views;
@@ -331,13 +348,7 @@ static int launch_head_gap_dense(kws_handle* h, Model& m, const void* act, bool 
   else launch_gemm_f32(LoadGap<float>{static_cast<const float*>(act), m.t_last, m.c_last}, m.w_d1, rows, m.hidden, m.c_last, e, st);
   KWS_T1(h, st);
   KWS_LAUNCH_CHECK(h);
-  const int grid = std::max(1, std::min(4 * h->num_sms, (n_clips + 7) / 8));
-  KWS_T0(h, KC_HEAD, st);
-  dense_softmax_tta_kernel<<<grid, 256, static_cast<size_t>(m.hidden) * m.classes * sizeof(float), st>>>(
-      m.hidden_ws, m.hidden, n_views, n_clips, m.w_d2, m.classes, probs_mean, argmax);
-  KWS_T1(h, st);
-  KWS_LAUNCH_CHECK(h);
-  return KWS_OK;
+  return launch_dense_softmax_tta(h, m.hidden_ws, m.hidden, n_views, n_clips, m.w_d2, m.classes, probs_mean, argmax, st);
 }
 
 int launch_to_float(kws_handle* h, const void* src, bool src_half, float* dst, size_t n, cudaStream_t st) {

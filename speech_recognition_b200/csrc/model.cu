@@ -41,6 +41,18 @@ void same_pad(int T, int k, int s, int* out, int* pad_left) {   // TF 'SAME'
 int model_build(kws_handle* h, int slot, int arch, const kws_tensor_h* t, int n) {
   if (slot < 0 || slot >= KWS_MAX_MODELS) return fail(h, KWS_EINVAL, "model slot out of range");
   const ArchSpec* spec = nullptr;
+  if (arch == KWS_ARCH_STEFFENET) {
+    Model& sm = h->models[slot];
+    if (sm.blob) { cudaFree(sm.blob); sm.blob = nullptr; }
+    if (sm.tc_blob) { cudaFree(sm.tc_blob); sm.tc_blob = nullptr; }
+    if (sm.hidden_ws) { cudaFree(sm.hidden_ws); sm.hidden_ws = nullptr; }
+    if (sm.steffe) { steffe_free(sm.steffe); sm.steffe = nullptr; }
+    sm = Model();
+    sm.arch = arch;
+    const int rc = steffe_build(h, sm, t, n);
+    if (rc == KWS_OK) sm.loaded = true;
+    return rc;
+  }
   if (arch == KWS_ARCH_195 || arch == 206) spec = &kArch195;
   else if (arch == KWS_ARCH_106) spec = &kArch106;
   else if (arch == KWS_ARCH_TIME_SLICED) spec = &kArchTimeSliced;
@@ -65,6 +77,7 @@ int model_build(kws_handle* h, int slot, int arch, const kws_tensor_h* t, int n)
   if (m.blob) { cudaFree(m.blob); m.blob = nullptr; }
   if (m.tc_blob) { cudaFree(m.tc_blob); m.tc_blob = nullptr; }
   if (m.hidden_ws) { cudaFree(m.hidden_ws); m.hidden_ws = nullptr; }
+  if (m.steffe) { steffe_free(m.steffe); m.steffe = nullptr; }
   m = Model();
   m.arch = arch; m.classes = spec->classes; m.c0 = spec->conv1;
   m.dense1_bias = spec->bias; m.pool_max_avg = spec->max_avg;

@@ -134,7 +134,7 @@ def raw_synthetic_weights(arch: int, seed: int | None = None, head_gain: float |
     """Seeded Glorot-uniform kernels with *uncalibrated* BatchNorm statistics."""
     rs = np.random.RandomState(arch if seed is None else seed)
     if head_gain is None:
-        head_gain = {"attn_mean": 32.0, "gap_dense": 4.0}.get(ARCHS[arch]["pool"], 6.0)
+        head_gain = {"attn_mean": 32.0, "gap_dense": 4.0, "max_avg_dense": 2.0}.get(ARCHS[arch]["pool"], 6.0)
     w = {}
     for name, shp in weight_shapes(arch).items():
         if name.endswith("/gamma"):
@@ -149,9 +149,9 @@ def raw_synthetic_weights(arch: int, seed: int | None = None, head_gain: float |
             rf = int(np.prod(shp[:-2])) if len(shp) > 2 else 1
             lim = np.sqrt(6.0 / (rf * shp[-2] + rf * shp[-1]))
             v = rs.uniform(-lim, lim, shp)
-            if name == "dense_2/kernel":
+            if name == "dense_2/kernel" or (name == "dense_1/kernel" and ARCHS[arch]["pool"] == "max_avg_dense"):
                 v = v * head_gain      # trained-classifier contrast instead of a near-uniform softmax
-            if name == "dense_1/kernel":
+            if name == "dense_1/kernel" and ARCHS[arch]["pool"] != "max_avg_dense":
                 v = v * attn_gain
         w[name] = v.astype(np.float32)
     return w
@@ -178,6 +178,8 @@ def synthetic_weights(arch: int, calibrated: bool = True):
     BatchNorm moving statistics come from ``data/synth_bn_<arch>.npz``."""
     key = 195 if arch == 206 else arch
     w = raw_synthetic_weights(arch)
+    if arch == 1663:                      # steffeNet: raw BatchNorm statistics (ReLU6 and the residual sums keep it in range)
+        return w
     if calibrated:
         path = os.path.join(_DATA, f"synth_bn_{key}.npz")
         if not os.path.exists(path):

@@ -13,6 +13,8 @@ from .arch import weight_shapes
 
 def infer_arch(weights: dict) -> int:
     c0 = weights["conv1d_1/kernel"].shape[-1]
+    if weights["conv1d_1/kernel"].shape[0] == 75 and "dense_2/kernel" not in weights:
+        return 1663                                  # steffeNet (model.py:1663-1726)
     classes = weights["dense_2/kernel"].shape[-1]
     if c0 == 128 and classes == 12:
         return 195

@@ -522,3 +522,26 @@ def test_time_sliced_family(engine):
     finally:
         engine.set_fusion(True)
         engine.set_precision("fp32")
+
+
+# --------------------------------------------------------------------------- steffeNet
+def test_steffenet_family(engine):
+    """steffeNet (model.py:1663-1726): k75 / s50 stem, SAME depthwise-separable blocks, strided 1x1 shortcuts with BN,
+    residual adds, channels to 1536, max || average pooling head -- on the fp32 CUDA-core kernels (both tiers), against
+    the float64 oracle, with TTA views, chunking (rows > max_rows) and the host entry point."""
+    w = synth.synthetic_weights(1663)
+    assert engine.load_model(3, 1663, w) == 12
+    x = synth.make_clips(70, seed=1663)                               # 70 clips x 8 views = 560 rows > max_rows 512
+    r_probs, r_pred = driver.tta_predict(lambda v: network.forward_steffenet(v, w), x[:20], TTA_8)
+    for prec in ("fp32", "tc"):
+        engine.set_precision(prec)
+        try:
+            probs, amax = engine.forward(dev(x), views=TTA_8, slot=3)
+        finally:
+            engine.set_precision("fp32")
+        np.testing.assert_allclose(probs.cpu().numpy()[:20], r_probs, rtol=1e-4, atol=1e-5)
+        assert np.array_equal(amax.cpu().numpy()[:20], r_pred)
+    one = network.forward_steffenet(x[20:30], w)
+    hp, ha = engine.predict_host(x[20:30], views=((0, 1.0),), slot=3)
+    np.testing.assert_allclose(hp, one, rtol=1e-4, atol=1e-5)
+    assert np.array_equal(ha, one.argmax(1))

@@ -248,3 +248,26 @@ def test_time_sliced_oracle_against_independent_torch_module():
     ref = torch.softmax(z @ torch.as_tensor(w["dense_2/kernel"]).double(), -1).numpy()
     got = network.forward(x.numpy(), w, 716, dtype=torch.float64)
     np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-12)
+
+
+def test_steffenet_oracle_structure():
+    """steffeNet restatement (model.py:1663-1726): layer-creation-order names (the shortcut Conv1D / BN of a stride-2 residual
+    block precede the block's own layers), lengths 320 -> 5, 20.1 M parameters, a probability vector; the product-side
+    shape table (arch.py) is the same table."""
+    import torch
+    from oracle import network
+    from speech_recognition_b200 import synth, arch
+    shapes = network.steffenet_weight_shapes(12)
+    assert list(shapes.items()) == list(arch.steffenet_weight_shapes(12).items())
+    assert shapes["conv1d_1/kernel"] == (75, 1, 256) and shapes["conv1d_3/kernel"] == (1, 256, 320)      # first shortcut
+    assert shapes["depthwise_conv2d_2/depthwise_kernel"] == (1, 3, 256, 1) and shapes["conv1d_4/kernel"] == (1, 256, 320)
+    assert shapes["conv1d_32/kernel"] == (1, 1536, 1536) and shapes["dense_1/kernel"] == (3072, 12) and len(shapes) == 186
+    assert sum(int(np.prod(v)) for v in shapes.values()) == 20102912
+    w = synth.synthetic_weights(1663)
+    x = synth.make_clips(2, seed=8)
+    p = network.forward_steffenet(x, w)
+    assert p.shape == (2, 12) and np.allclose(p.sum(1), 1.0) and np.isfinite(p).all()
+    # a roll by a multiple of the stem's stride (50) shifts the stem's output by whole frames: the pooled head is
+    # invariant up to the SAME-padding edges, so the label survives
+    q = network.forward_steffenet(np.roll(x, 100, axis=1), w)
+    assert np.array_equal(p.argmax(1), q.argmax(1))
