@@ -472,8 +472,10 @@ def run_config3(args):
                          "frac": blk_gbs / peaks["hbm_gbs"], "peak_source": peaks["source"] + " (copy bandwidth)",
                          "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                          "avg_launch_ms": blk_avg_launch_ms, "clip_views_per_launch": views_per_launch,
-                         "traffic": tr["bytes_per_launch"] if tr else None,
-                         "traffic_source": tr["source"] if tr else None,
+                         # the ncu capture was taken at 32,768 clip-views per launch; traffic is linear in the rows
+                         "traffic": tr["bytes_per_launch"] * views_per_launch / tr.get("clip_views_per_launch", views_per_launch) if tr else None,
+                         "traffic_source": (tr["source"] + "; scaled from %d to %d clip-views per launch" % (
+                             tr.get("clip_views_per_launch", views_per_launch), views_per_launch)) if tr else None,
                          "share_of_step": blk_ms / t_total if t_total else None,
                          "tensor_tflops": blk_tflops, "tensor_frac": blk_tflops / peaks["tflops"]},
             "secondary_rooflines": {
