@@ -152,11 +152,12 @@ int pipeline(kws_handle* h, const PipelineArgs& a) {
   // Chunks of one forward pass worth of clip-views (max_rows), so that with two staging slots
   // the H2D copy of chunk k+1 (copy stream) and the D2H copy of chunk k-1 (second copy stream)
   // run under the kernels of chunk k (compute stream); events order the three streams per slot.
-  // Clips per staged chunk.  A compute-bound call (8 TTA views: 30 us of kernels per clip against 1 us of copy) gains 2 % from
-  // 8,192-clip chunks (larger launches); a copy-bound one (3 views or fewer) loses 12 % to them (the first chunk's upload and
-  // the last chunk's download are the exposed part), r02 A/B.  KWS_HOST_CHUNK overrides.
+  // Clips per staged chunk (KWS_HOST_CHUNK overrides).  r02 A/B on one 8-GPU box, 16,384 clips x 8 views per call: 8,192-clip
+  // chunks are 2 % faster than 4,096-clip ones on one or two GPUs (larger launches) but slower from four GPUs on, where
+  // the ranks share the host's memory bandwidth and the exposed first upload / last download of a call grows with the
+  // chunk (3.65 M against 3.70 M clips/s on eight); copy-bound calls (3 views or fewer) lose 12 % to the larger chunk.
   static const int chunk_env = [] { const char* e = getenv("KWS_HOST_CHUNK"); return e && atoi(e) > 0 ? atoi(e) : 0; }();
-  const int chunk_cap = chunk_env ? chunk_env : (a.n_views >= 6 ? 8192 : 4096);
+  const int chunk_cap = chunk_env ? chunk_env : 4096;
   const int chunk = std::max(1, std::min(std::min(B, chunk_cap), do_fwd ? std::max(1, h->max_rows / a.n_views) : 2048));
   const StageLayout lay = stage_layout(chunk, std::max(classes, 1), fdim);
   int rc = ensure_bytes(h, &h->stage_d, &h->stage_bytes, 2 * lay.total);
