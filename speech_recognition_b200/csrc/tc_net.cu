@@ -64,7 +64,7 @@ template <int MODE> struct Roles {
   static constexpr int RAW_WARP = MODE == 0 ? -1 : EPI_WARPS + 2;
   static constexpr int PROD_WARP0 = MODE == 0 ? EPI_WARPS + 2 : EPI_WARPS + 3;
   static constexpr int PROD_WARPS = MODE == 0 ? 6 : 8;
-  static constexpr int PROD_THREADS = PROD_WARPS * 32;           // 192 / 256
+  [[maybe_unused]] static constexpr int PROD_THREADS = PROD_WARPS * 32;           // 192 / 256
   static constexpr int THREADS = 32 * (PROD_WARP0 + PROD_WARPS); // 512 / 608
 };
 constexpr int NUM_PROD_THREADS = Roles<1>::PROD_THREADS;         // dw_pw: 256
@@ -606,7 +606,6 @@ __global__ void __launch_bounds__(Roles<MODE>::THREADS, 1) tc_gemm_kernel(const 
       const bool resident = ((p.b_resident) + zi) != 0, ko_mma = kProfile && ((p.knockout & 4) + zi) != 0;
       const uint32_t tmem0 = ((tmem_base) + zi);
       int sa = 0; uint32_t pa = 0; int sb = 0; uint32_t pb = 0; int acc = 0; uint32_t acc_phase = 0;
-      int tcnt = 0, tn = 0;
       if (resident && tile0 < num_tiles) {                       // the weights arrive once per launch
         for (int j = 0; j < blocks_per_tile; ++j) mbar_wait(&b_full[j], 0);
       }
@@ -971,11 +970,6 @@ __device__ __forceinline__ uint4 pack8_relu6(const uint32_t* v, const float* sh,
   return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-__device__ __forceinline__ uint4 shfl_down4(const uint4& v, int d) {
-  return make_uint4(__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d),
-                    __shfl_down_sync(0xffffffffu, v.z, d), __shfl_down_sync(0xffffffffu, v.w, d));
-}
-
 // fp16 x fp16 + fp32 -> fp32 with the halves picked from packed registers (FHFMA with .H0 / .H1 operand selectors)
 #define KWS_FHFMA(AH, BH)                                                                                   \
   asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\t"                     \
@@ -1012,7 +1006,7 @@ __global__ void __launch_bounds__(FuseRoles<kT>::THREADS, 1) conv1_block1_kernel
   uint8_t* a2_base = smem + lay.a2;
   uint8_t* out_base = smem + lay.out;
   uint8_t* win_base = smem + lay.win;
-  uint8_t* raw_base = smem + lay.raw;
+  [[maybe_unused]] uint8_t* raw_base = smem + lay.raw;   // (row-major form only)
   float* s_sh1 = reinterpret_cast<float*>(smem + lay.sh1);
   float* s_sh2 = reinterpret_cast<float*>(smem + lay.sh2);
   __half* s_taps = reinterpret_cast<__half*>(smem + lay.taps);
