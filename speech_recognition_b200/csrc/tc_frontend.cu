@@ -70,7 +70,7 @@ __host__ __device__ inline FSmem f_smem(int n_mel, bool mfcc, int b_stages) {
   FSmem s; uint32_t o = 0;
   s.a_off = o; o += F_A_STAGES * F_A_STAGE;
   s.b_off = o; o += static_cast<uint32_t>(b_stages) * F_B_BLOCK;
-  s.tab_off = o; o += F_BINS * 16;
+  s.tab_off = o; o += (F_BINS + 1) * 16;                            // + one pad entry: the epilogue loads one bin ahead
   s.dct_off = o; o += mfcc ? static_cast<uint32_t>(n_mel) * F_DCT_LD * 4u : 0u;
   s.part_off = o; o += static_cast<uint32_t>(n_mel + 2) * TILE_M * 4u;   // linear mel sums [n_mel][128 rows] + 2 overlap rows
   s.bar_off = o; o += (2 * F_A_STAGES + 2 * F_B_STAGES + 2) * 8 + 16;
@@ -87,8 +87,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) stft_mel_tc_kernel(const DftPara
   uint8_t* b_base = smem + lay.b_off;
   float4* s_tab = reinterpret_cast<float4*>(smem + lay.tab_off);
   float* s_dct = reinterpret_cast<float*>(smem + lay.dct_off);
-  float* s_part = reinterpret_cast<float*>(smem + lay.part_off);  // [n_mel][128]
-  float* s_ovl = s_part + p.n_mel * TILE_M;                        // [2][128]: second half's share of filters m_split, m_split + 1
+  float* s_part = reinterpret_cast<float*>(smem + lay.part_off);  // [n_mel + 2][128] linear mel sums, see the epilogue
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_off);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + F_A_STAGES;
@@ -100,7 +99,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) stft_mel_tc_kernel(const DftPara
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  for (int i = tid; i < F_BINS; i += F_THREADS) s_tab[i] = p.bin_tab[i];
+  for (int i = tid; i <= F_BINS; i += F_THREADS) s_tab[i] = i < F_BINS ? p.bin_tab[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   if (MFCC)
     for (int i = tid; i < p.n_mel * F_DCT_LD; i += F_THREADS) s_dct[i] = p.dct[i];
   if (warp == F_MMA_WARP) {
@@ -133,49 +132,62 @@ __global__ void __launch_bounds__(F_THREADS, 1) stft_mel_tc_kernel(const DftPara
       const bool ok = R < p.rows_total;
       float* orow = p.out + R * out_dim;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(hh * 256);
+      // Banded mel with two running sums per thread: acc_a = filter m, acc_b = filter m + 1; when the table says
+      // "advance" the finished filter goes to shared memory.  Half hh writes its linear sums to rows
+      // [m + 2 hh] of s_part: half 0 owns filters 0 .. m_split + 1 (rows 0 .. m_split + 1), half 1 owns filters
+      // m_split .. n_mel - 1 (rows m_split + 2 .. n_mel + 1), so the store address is one pointer that moves by a row
+      // per finished filter and the two filters that straddle bin 128 are summed by the reader in a fixed order.
+      // (r02: the first version kept a filter index, a bounds check and the straddle case inside the per-bin code;
+      // unrolled 128 times that was 72 KB of instructions, and the warps sat in instruction-cache misses -- stall_no_inst
+      // was a third of the samples of this loop, which ran at ~250 cycles per bin.  Now the per-bin hot path is
+      // LDS / FFMA / MUFU / 2 FFMA + one never-mispredicted uniform branch, the table entry is loaded one bin ahead,
+      // and the column loop is not unrolled.)
       float acc_a = 0.0f, acc_b = 0.0f;
-      int m_cur = hh ? p.m_split : 0;
-      auto emit = [&]() {                                        // filter m_cur is complete for this half
-        if (m_cur < p.n_mel) {
-          float* dst = (hh && m_cur <= p.m_split + 1) ? s_ovl + (m_cur - p.m_split) * TILE_M : s_part + m_cur * TILE_M;
-          dst[row] = acc_a;
-        }
-        acc_a = acc_b; acc_b = 0.0f; ++m_cur;
-      };
-      auto bins16 = [&](const uint32_t (&v)[32], int bin0) {
+      float* dst = s_part + static_cast<size_t>((hh ? p.m_split + 2 : 0)) * TILE_M + row;
+      const float4* tab = s_tab + hh * (F_BINS / 2);
+      float4 e = tab[0];
+      auto bins16 = [&](const uint32_t (&v)[32], const float4* t) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          const float4 e = s_tab[bin0 + k];
-          for (int adv = __float_as_int(e.z); adv > 0; --adv) emit();      // warp-uniform
+          const float4 en = t[k + 1];                                        // next bin's entry (the table has one pad entry)
+          int adv = __float_as_int(e.z);                                     // warp-uniform, non-zero for n_mel of the 256 bins
+          if (adv) {
+#pragma unroll 1
+            do { *dst = acc_a; dst += TILE_M; acc_a = acc_b; acc_b = 0.0f; } while (--adv);
+          }
           const float re = __uint_as_float(v[2 * k]), im = __uint_as_float(v[2 * k + 1]);
           float mag;                                                         // ComplexAbs, input_data.py:366
-          asm("sqrt.approx.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(re, re, im * im)));   // MUFU.SQRT: 1 ulp-class, far inside the 1e-4 tier
+          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(re, re, im * im)));   // MUFU.SQRT: 1 ulp-class, far inside the 1e-4 tier
           acc_a = fmaf(mag, e.x, acc_a);
           acc_b = fmaf(mag, e.y, acc_b);
+          e = en;
         }
       };
       {                                                          // next TMEM load in flight during the math
         uint32_t va[32], vb[32];
         tmem_ld32(taddr, va);
+#pragma unroll 1
         for (int c0 = 0; c0 < 256; c0 += 64) {
           tmem_ld_wait();
           tmem_ld32(taddr + c0 + 32, vb);
-          bins16(va, hh * 128 + c0 / 2);
+          bins16(va, tab + c0 / 2);
           tmem_ld_wait();
           if (c0 + 64 < 256) tmem_ld32(taddr + c0 + 64, va);
-          bins16(vb, hh * 128 + c0 / 2 + 16);
+          bins16(vb, tab + c0 / 2 + 16);
         }
       }
       tc_fence_before();
       mbar_arrive(acc_empty);                                    // TMEM is free for the next tile
       acc_phase ^= 1;
-      if (hh == 0) { emit(); emit(); }                           // flush the two open filters m_split, m_split + 1
-      else while (m_cur < p.n_mel) emit();
+      {                                                          // flush: half 0 its two open filters, half 1 every filter that is left
+        const int m_open = static_cast<int>((dst - (s_part + row)) / TILE_M) - 2 * hh;
+        const int m_end = hh ? p.n_mel : min(p.n_mel, m_open + 2);
+        for (int m = m_open; m < m_end; ++m) { *dst = acc_a; dst += TILE_M; acc_a = acc_b; acc_b = 0.0f; }
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(F_EPI_WARPS * 32) : "memory");    // all linear mel sums of the tile are in smem
       auto log_mel = [&](int m) {
-        float v = s_part[m * TILE_M + row];
-        if (m == p.m_split) v += s_ovl[row];
-        if (m == p.m_split + 1) v += s_ovl[TILE_M + row];
+        float v = m <= p.m_split + 1 ? s_part[m * TILE_M + row] : 0.0f;           // first bin half's share
+        if (m >= p.m_split) v += s_part[(m + 2) * TILE_M + row];                  // second half's share
         return FLOOR ? logf(fmaxf(v, 1e-12f)) : logf(v + 1e-6f);             // TF mfcc.cc / input_data.py:378
       };
       if (MFCC) {                                                // this thread: DCT outputs [32 hh, 32 hh + 32) of its row
