@@ -55,7 +55,8 @@ struct DftParams {
   const float* wav;          // [B, 16000]
   float* out;                // [rows_total, out_dim]
   const uint8_t* b_img;      // basis blocks, index ((kb * 2 + nh) * 2 + part), part 0 = hi, 1 = lo
-  const float4* bin_tab;     // [256] {w_a, w_b, advance (int bits), 0}
+  const float2* bin_tab;     // [256] {w_a, w_b}: weights of the bin for the open filter pair (m, m + 1), then
+                             // [16] uint32: 2 bits per bin = how many filters finish BEFORE the bin (0..3)
   const float* dct;          // [n_mel][64] zero padded
   int frames, hop, win, n_mel, n_keep;
   int rows_total, num_tiles, num_kb, last_ksteps;
@@ -70,7 +71,7 @@ __host__ __device__ inline FSmem f_smem(int n_mel, bool mfcc, int b_stages) {
   FSmem s; uint32_t o = 0;
   s.a_off = o; o += F_A_STAGES * F_A_STAGE;
   s.b_off = o; o += static_cast<uint32_t>(b_stages) * F_B_BLOCK;
-  s.tab_off = o; o += (F_BINS + 1) * 16;                            // + one pad entry: the epilogue loads one bin ahead
+  s.tab_off = o; o += F_BINS * 8 + (F_BINS / 16) * 4;               // weight pairs + advance words
   s.dct_off = o; o += mfcc ? static_cast<uint32_t>(n_mel) * F_DCT_LD * 4u : 0u;
   s.part_off = o; o += static_cast<uint32_t>(n_mel + 2) * TILE_M * 4u;   // linear mel sums [n_mel][128 rows] + 2 overlap rows
   s.bar_off = o; o += (2 * F_A_STAGES + 2 * F_B_STAGES + 2) * 8 + 16;
@@ -85,7 +86,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) stft_mel_tc_kernel(const DftPara
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_base = smem + lay.a_off;
   uint8_t* b_base = smem + lay.b_off;
-  float4* s_tab = reinterpret_cast<float4*>(smem + lay.tab_off);
+  float2* s_w = reinterpret_cast<float2*>(smem + lay.tab_off);
+  uint32_t* s_adv = reinterpret_cast<uint32_t*>(s_w + F_BINS);
   float* s_dct = reinterpret_cast<float*>(smem + lay.dct_off);
   float* s_part = reinterpret_cast<float*>(smem + lay.part_off);  // [n_mel + 2][128] linear mel sums, see the epilogue
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_off);
@@ -99,7 +101,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) stft_mel_tc_kernel(const DftPara
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  for (int i = tid; i <= F_BINS; i += F_THREADS) s_tab[i] = i < F_BINS ? p.bin_tab[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < F_BINS; i += F_THREADS) s_w[i] = p.bin_tab[i];
+  if (tid < F_BINS / 16) s_adv[tid] = reinterpret_cast<const uint32_t*>(p.bin_tab + F_BINS)[tid];
   if (MFCC)
     for (int i = tid; i < p.n_mel * F_DCT_LD; i += F_THREADS) s_dct[i] = p.dct[i];
   if (warp == F_MMA_WARP) {
@@ -139,41 +142,48 @@ __global__ void __launch_bounds__(F_THREADS, 1) stft_mel_tc_kernel(const DftPara
       // per finished filter and the two filters that straddle bin 128 are summed by the reader in a fixed order.
       // (r02: the first version kept a filter index, a bounds check and the straddle case inside the per-bin code;
       // unrolled 128 times that was 72 KB of instructions, and the warps sat in instruction-cache misses -- stall_no_inst
-      // was a third of the samples of this loop, which ran at ~250 cycles per bin.  Now the per-bin hot path is
-      // LDS / FFMA / MUFU / 2 FFMA + one never-mispredicted uniform branch, the table entry is loaded one bin ahead,
-      // and the column loop is not unrolled.)
+      // was a third of the samples of this loop, which ran at ~250 cycles per bin.  Now 8 bins are one unit: their
+      // weight pairs are loaded and their magnitudes computed first (8 independent FMUL / FFMA / MUFU.SQRT, so the MUFU
+      // and LDS latencies are paid once per unit, not per bin), then per bin two FFMAs and one warp-uniform branch
+      // whose predicate is a bit test on a register (the advance counts of 16 bins are one word); the column loop is
+      // not unrolled.)
       float acc_a = 0.0f, acc_b = 0.0f;
       float* dst = s_part + static_cast<size_t>((hh ? p.m_split + 2 : 0)) * TILE_M + row;
-      const float4* tab = s_tab + hh * (F_BINS / 2);
-      float4 e = tab[0];
-      auto bins16 = [&](const uint32_t (&v)[32], const float4* t) {
+      const float2* wtab = s_w + hh * (F_BINS / 2);
+      const uint32_t* advw = s_adv + hh * (F_BINS / 32);
+      auto bins8 = [&](const uint32_t (&v)[16], const float2* wp, uint32_t bits) {   // bits: 2 per bin, bin 0 in bits 0-1
+        float2 w[8];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const float4 en = t[k + 1];                                        // next bin's entry (the table has one pad entry)
-          int adv = __float_as_int(e.z);                                     // warp-uniform, non-zero for n_mel of the 256 bins
-          if (adv) {
+        for (int k = 0; k < 8; ++k) w[k] = wp[k];
+        float mag[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {                                        // ComplexAbs, input_data.py:366
+          const float re = __uint_as_float(v[2 * k]), im = __uint_as_float(v[2 * k + 1]);
+          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mag[k]) : "f"(fmaf(re, re, im * im)));   // MUFU.SQRT: 1 ulp-class, far inside the 1e-4 tier
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (bits & (3u << (2 * k))) {                                      // warp-uniform; taken for n_mel of the 256 bins
+            int adv = static_cast<int>((bits >> (2 * k)) & 3u);
 #pragma unroll 1
             do { *dst = acc_a; dst += TILE_M; acc_a = acc_b; acc_b = 0.0f; } while (--adv);
           }
-          const float re = __uint_as_float(v[2 * k]), im = __uint_as_float(v[2 * k + 1]);
-          float mag;                                                         // ComplexAbs, input_data.py:366
-          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mag) : "f"(fmaf(re, re, im * im)));   // MUFU.SQRT: 1 ulp-class, far inside the 1e-4 tier
-          acc_a = fmaf(mag, e.x, acc_a);
-          acc_b = fmaf(mag, e.y, acc_b);
-          e = en;
+          acc_a = fmaf(mag[k], w[k].x, acc_a);
+          acc_b = fmaf(mag[k], w[k].y, acc_b);
         }
       };
-      {                                                          // next TMEM load in flight during the math
-        uint32_t va[32], vb[32];
-        tmem_ld32(taddr, va);
+      {                                                          // next TMEM load (16 columns = 8 bins) in flight during the math
+        uint32_t va[16], vb[16];
+        tmem_ld16(taddr, va);
 #pragma unroll 1
-        for (int c0 = 0; c0 < 256; c0 += 64) {
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+          const uint32_t bits = advw[c0 >> 5];
           tmem_ld_wait();
-          tmem_ld32(taddr + c0 + 32, vb);
-          bins16(va, tab + c0 / 2);
+          tmem_ld16(taddr + c0 + 16, vb);
+          bins8(va, wtab + c0 / 2, bits);
           tmem_ld_wait();
-          if (c0 + 64 < 256) tmem_ld32(taddr + c0 + 64, va);
-          bins16(vb, tab + c0 / 2 + 16);
+          if (c0 + 32 < 256) tmem_ld16(taddr + c0 + 32, va);
+          bins8(vb, wtab + c0 / 2 + 8, bits >> 16);
         }
       }
       tc_fence_before();
@@ -347,7 +357,8 @@ int frontend_build_tc(kws_handle* h, const float* basis, const float* mel, const
   if (fe.win % 8 || fe.hop % 4 || fe.n_fft != 512 || fe.n_keep > F_DCT_LD || fe.n_mel > 128) return KWS_OK;
   const int nb = fe.n_bins, num_kb = (fe.win + SLAB_K - 1) / SLAB_K;
   // ---- banded mel: every bin feeds at most two adjacent filters (m, m+1), m non-decreasing ----
-  std::vector<float> tab(static_cast<size_t>(F_BINS) * 4, 0.0f);
+  std::vector<float> tab(static_cast<size_t>(F_BINS) * 2 + F_BINS / 16, 0.0f);   // weight pairs, then the advance words
+  std::vector<uint32_t> advw(F_BINS / 16, 0u);
   int m_cur = 0;
   fe.tc_m_split = 0;
   for (int j = 0; j < nb; ++j) {
@@ -360,13 +371,15 @@ int frontend_build_tc(kws_handle* h, const float* basis, const float* mel, const
     if (lo >= 0) {
       if (hi - lo > 1) return KWS_OK;                               // not banded: fp32 chain
       adv = std::max(0, hi - 1 - m_cur);
+      if (adv > 3) return KWS_OK;                                   // two bits per bin in the advance words: fp32 chain
       m_cur += adv;
       if (lo < m_cur || hi > m_cur + 1) return KWS_OK;
-      tab[4 * j + 0] = mel[static_cast<size_t>(j) * fe.n_mel + m_cur];
-      tab[4 * j + 1] = m_cur + 1 < fe.n_mel ? mel[static_cast<size_t>(j) * fe.n_mel + m_cur + 1] : 0.0f;
+      tab[2 * j + 0] = mel[static_cast<size_t>(j) * fe.n_mel + m_cur];
+      tab[2 * j + 1] = m_cur + 1 < fe.n_mel ? mel[static_cast<size_t>(j) * fe.n_mel + m_cur + 1] : 0.0f;
     }
-    std::memcpy(&tab[4 * j + 2], &adv, sizeof(int));
+    advw[j / 16] |= static_cast<uint32_t>(adv) << (2 * (j % 16));
   }
+  std::memcpy(&tab[static_cast<size_t>(F_BINS) * 2], advw.data(), advw.size() * sizeof(uint32_t));
   // ---- split-fp16 basis blocks ----
   const size_t n_blocks = static_cast<size_t>(num_kb) * 4;
   std::vector<__half> img(n_blocks * F_B_BLOCK / 2, __float2half_rn(0.0f));
@@ -412,7 +425,7 @@ int launch_features_tc(kws_handle* h, const float* wav, int B, int kind, float* 
   DftParams p{};
   p.wav = wav; p.out = out;
   p.b_img = fe.tc_basis;
-  p.bin_tab = reinterpret_cast<const float4*>(fe.tc_bin_tab);
+  p.bin_tab = reinterpret_cast<const float2*>(fe.tc_bin_tab);
   p.dct = fe.tc_dct;
   p.frames = fe.frames; p.hop = fe.hop; p.win = fe.win; p.n_mel = fe.n_mel; p.n_keep = fe.n_keep;
   p.rows_total = B * fe.frames;
