@@ -144,11 +144,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) stft_mel_tc_kernel(const DftPara
       // unrolled 128 times that was 72 KB of instructions, and the warps sat in instruction-cache misses -- stall_no_inst
       // was a third of the samples of this loop, which ran at ~250 cycles per bin.  Now 8 bins are one unit: their
       // weight pairs are loaded and their magnitudes computed first (8 independent FMUL / FFMA / MUFU.SQRT, so the MUFU
-      // and LDS latencies are paid once per unit, not per bin), then per bin two FFMAs and one warp-uniform branch
-      // whose predicate is a bit test on a register (the advance counts of 16 bins are one word); the column loop is
-      // not unrolled.)
+      // and LDS latencies are paid once per unit, not per bin), then per bin two FFMAs and a predicated advance whose
+      // predicate is a bit test on a register (the advance counts of 16 bins are one word); the column loop is not
+      // unrolled.)
       float acc_a = 0.0f, acc_b = 0.0f;
-      float* dst = s_part + static_cast<size_t>((hh ? p.m_split + 2 : 0)) * TILE_M + row;
+      uint32_t di = static_cast<uint32_t>((hh ? p.m_split + 2 : 0) * TILE_M + row);   // s_part index of the open filter's sum
       const float2* wtab = s_w + hh * (F_BINS / 2);
       const uint32_t* advw = s_adv + hh * (F_BINS / 32);
       auto bins8 = [&](const uint32_t (&v)[16], const float2* wp, uint32_t bits) {   // bits: 2 per bin, bin 0 in bits 0-1
@@ -161,15 +161,30 @@ __global__ void __launch_bounds__(F_THREADS, 1) stft_mel_tc_kernel(const DftPara
           const float re = __uint_as_float(v[2 * k]), im = __uint_as_float(v[2 * k + 1]);
           asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(mag[k]) : "f"(fmaf(re, re, im * im)));   // MUFU.SQRT: 1 ulp-class, far inside the 1e-4 tier
         }
+        if ((bits & 0xAAAAu) == 0u) {
+          // no bin of the unit finishes more than one filter (always, unless the filters are narrower than a bin):
+          // branch-free -- a GPU does not predict branches, and a warp-uniform branch per bin cost more than the math
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          if (bits & (3u << (2 * k))) {                                      // warp-uniform; taken for n_mel of the 256 bins
-            int adv = static_cast<int>((bits >> (2 * k)) & 3u);
-#pragma unroll 1
-            do { *dst = acc_a; dst += TILE_M; acc_a = acc_b; acc_b = 0.0f; } while (--adv);
+          for (int k = 0; k < 8; ++k) {
+            const bool adv = ((bits >> (2 * k)) & 1u) != 0u;
+            if (adv) s_part[di] = acc_a;                                     // predicated store
+            di += adv ? TILE_M : 0;
+            acc_a = adv ? acc_b : acc_a;
+            acc_b = adv ? 0.0f : acc_b;
+            acc_a = fmaf(mag[k], w[k].x, acc_a);
+            acc_b = fmaf(mag[k], w[k].y, acc_b);
           }
-          acc_a = fmaf(mag[k], w[k].x, acc_a);
-          acc_b = fmaf(mag[k], w[k].y, acc_b);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (bits & (3u << (2 * k))) {                                    // warp-uniform
+              int adv = static_cast<int>((bits >> (2 * k)) & 3u);
+#pragma unroll 1
+              do { s_part[di] = acc_a; di += TILE_M; acc_a = acc_b; acc_b = 0.0f; } while (--adv);
+            }
+            acc_a = fmaf(mag[k], w[k].x, acc_a);
+            acc_b = fmaf(mag[k], w[k].y, acc_b);
+          }
         }
       };
       {                                                          // next TMEM load (16 columns = 8 bins) in flight during the math
@@ -190,9 +205,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) stft_mel_tc_kernel(const DftPara
       mbar_arrive(acc_empty);                                    // TMEM is free for the next tile
       acc_phase ^= 1;
       {                                                          // flush: half 0 its two open filters, half 1 every filter that is left
-        const int m_open = static_cast<int>((dst - (s_part + row)) / TILE_M) - 2 * hh;
+        const int m_open = static_cast<int>(di / TILE_M) - 2 * hh;
         const int m_end = hh ? p.n_mel : min(p.n_mel, m_open + 2);
-        for (int m = m_open; m < m_end; ++m) { *dst = acc_a; dst += TILE_M; acc_a = acc_b; acc_b = 0.0f; }
+        for (int m = m_open; m < m_end; ++m) { s_part[di] = acc_a; di += TILE_M; acc_a = acc_b; acc_b = 0.0f; }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(F_EPI_WARPS * 32) : "memory");    // all linear mel sums of the tile are in smem
       auto log_mel = [&](int m) {
