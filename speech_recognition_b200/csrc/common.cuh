@@ -78,7 +78,8 @@ struct Frontend {
   const uint8_t* tc_basis = nullptr;
   const float* tc_bin_tab = nullptr;
   const float* tc_dct = nullptr;
-  int tc_kblocks = 0, tc_last_ksteps = 0, tc_m_split = 0;
+  const float* tc_hann = nullptr;         // [512] window, zero padded
+  int tc_m_split = 0;
 };
 
 }  // namespace kws

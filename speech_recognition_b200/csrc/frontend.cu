@@ -16,7 +16,7 @@
 
 namespace kws {
 
-int frontend_build_tc(kws_handle* h, const float* basis, const float* mel, const float* dct);   // tc_frontend.cu
+int frontend_build_tc(kws_handle* h, const float* hann, const float* mel, const float* dct);   // tc_frontend.cu
 
 int frontend_build(kws_handle* h, int win, int hop, int n_mel, int n_keep, float f_lo, float f_hi,
                    int sample_rate, int flavour) {
@@ -126,7 +126,7 @@ int frontend_build(kws_handle* h, int win, int hop, int n_mel, int n_keep, float
   fe.dft_basis = fe.blob + o_basis;
   fe.mel_w = fe.blob + o_mel;
   fe.dct_w = fe.blob + o_dct;
-  int rc = frontend_build_tc(h, host.data() + o_basis, host.data() + o_mel, host.data() + o_dct);
+  int rc = frontend_build_tc(h, hann.data(), host.data() + o_mel, host.data() + o_dct);
   if (rc) return rc;
   fe.configured = true;
   return KWS_OK;
