@@ -267,6 +267,11 @@ class Ctx:
             dist.init_process_group("nccl", device_id=torch.device(f"cuda:{self.local}"))
         self.dev = torch.device(f"cuda:{self.local}")
         self.args = args
+        # clips per staged chunk of the *_host entry points (libkws reads the variable once): 8,192-clip chunks are ~3 %
+        # faster on one or two GPUs (larger launches), 4,096-clip ones from four GPUs on, where the ranks share the
+        # host's memory bandwidth and the exposed first upload / last download grows with the chunk (r02n / r02r A/B)
+        os.environ.setdefault("KWS_HOST_CHUNK", "8192" if self.world <= 2 else "4096")
+        self.host_chunk = int(os.environ["KWS_HOST_CHUNK"])
 
     def sync_all(self):
         self.torch.cuda.synchronize()
@@ -334,7 +339,7 @@ def base_line(ctx, args, value, ms, steps, config_extra, dtype="f16"):
         "warmup": max(args.warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": dtype if args.precision == "tc" else "f32", "data": "synthetic",
         "config": dict({"workload": WORKLOADS[args.config], "precision": args.precision, "max_rows": args.max_rows,
-                        "job_clips": N_CLIPS_JOB, "numa": ctx.numa}, **config_extra),
+                        "job_clips": N_CLIPS_JOB, "numa": ctx.numa, "host_chunk_clips": ctx.host_chunk}, **config_extra),
     }
 
 
@@ -559,9 +564,10 @@ def run_config2(args):
                          "bound": "tensor", "achieved": fe_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
                          "frac": fe_tflops / peaks["tflops"], "peak_source": peaks["source"] + " (sustained bf16)",
                          "algorithmic_flop_per_launch": FLOP_FRONTEND * B, "avg_launch_ms": dft_ms / max(dft_n, 1),
-                         "executed_flop_factor": 3.0, "traffic": None,
-                         "note": "algorithmic = one DFT-as-GEMM per clip (SURVEY 8d: 50.7 MFLOP); the kernel executes 3 fp16 "
-                                 "products per fp32-accurate product, so the tensor pipe does 3x this"},
+                         "executed_flop_factor": 1.5, "traffic": None,
+                         "note": "algorithmic = one K = 480, N = 514 DFT-as-GEMM per clip (SURVEY 8d: 50.7 MFLOP); the kernel "
+                                 "takes one radix-2 step out of it (half the products) and executes 3 fp16 products per "
+                                 "fp32-accurate product, so the tensor pipe does 1.5x this"},
             "secondary_rooflines": {
                 "whole_step_hbm_frac": BYTES_FRONTEND * B * args.steps / (ms / 1e3) / 1e9 / peaks["hbm_gbs"],
                 "whole_step_tensor_frac": FLOP_FRONTEND * B * args.steps / (ms / 1e3) / 1e12 / peaks["tflops"],

@@ -78,15 +78,33 @@ head_kernel(const TAct* __restrict__ act, int C, int n_views, int n_clips, const
   float* pv = w2t + classes * feat;                     // [clips per iteration][n_views][32] per-view probabilities
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int idx = tid; idx < n * HEAD_T; idx += HEAD_WARPS * 32) {          // dense_1 [n][9] -> [k][e][j groups][lane]
-    const int i = idx / HEAD_T, j = idx - i * HEAD_T;
-    const int k = i / HEAD_BLK, r = i - k * HEAD_BLK, ln = r >> 3, e = r & 7;
-    float* row = w1 + (k * 8 + e) * HEAD_WROW;
-    row[j < 4 ? ln * 4 + j : (j < 8 ? 128 + ln * 4 + (j - 4) : 256 + ln)] = __ldg(&w_d1[idx]);
+  // eight loads in flight per thread: with one dependent L2 round trip per element this prologue was 13 % of the
+  // launch (r02q profile)
+  constexpr int NT = HEAD_WARPS * 32, PF = 8;
+  for (int base = tid; base < n * HEAD_T; base += PF * NT) {               // dense_1 [n][9] -> [k][e][j groups][lane]
+    float v[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) { const int idx = base + u * NT; v[u] = idx < n * HEAD_T ? __ldg(&w_d1[idx]) : 0.0f; }
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int idx = base + u * NT;
+      if (idx < n * HEAD_T) {
+        const int i = idx / HEAD_T, j = idx - i * HEAD_T;
+        const int k = i / HEAD_BLK, r = i - k * HEAD_BLK, ln = r >> 3, e = r & 7;
+        float* row = w1 + (k * 8 + e) * HEAD_WROW;
+        row[j < 4 ? ln * 4 + j : (j < 8 ? 128 + ln * 4 + (j - 4) : 256 + ln)] = v[u];
+      }
+    }
   }
-  for (int i = tid; i < feat * classes; i += HEAD_WARPS * 32) {
-    const int r = i / classes, j = i - r * classes;
-    w2t[j * feat + r] = __ldg(&w_d2[i]);
+  for (int base = tid; base < feat * classes; base += PF * NT) {
+    float v[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) { const int i = base + u * NT; v[u] = i < feat * classes ? __ldg(&w_d2[i]) : 0.0f; }
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int i = base + u * NT;
+      if (i < feat * classes) { const int r = i / classes, j = i - r * classes; w2t[j * feat + r] = v[u]; }
+    }
   }
   const float bias = lane < HEAD_T ? __ldg(&b_d1[lane]) : 0.0f;
   __syncthreads();
