@@ -270,7 +270,8 @@ class Ctx:
         # clips per staged chunk of the *_host entry points (libkws reads the variable once): 8,192-clip chunks are ~3 %
         # faster on one or two GPUs (larger launches), 4,096-clip ones from four GPUs on, where the ranks share the
         # host's memory bandwidth and the exposed first upload / last download grows with the chunk (r02n / r02r A/B)
-        os.environ.setdefault("KWS_HOST_CHUNK", "8192" if self.world <= 2 else "4096")
+        # (config 3 only: the copy-bound 3-view configs 4 / 5 lose 10-15 % to the larger chunk)
+        os.environ.setdefault("KWS_HOST_CHUNK", "8192" if (self.world <= 2 and args.config == 3) else "4096")
         self.host_chunk = int(os.environ["KWS_HOST_CHUNK"])
 
     def sync_all(self):
